@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Benchmark of the SELD feature front-end hot path (BASELINE.json metric: audio-seconds/sec,
+log-mel + IV, 4 ch 24 kHz; % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the fused extractor over one batch of synthetic clips (BASELINE cfg2:
+B=64 x 10 s x 4 ch @ 24 kHz per GPU; weak scaling: every rank owns its own 64 clips, no
+data-path collective).  Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, HOP, NFFT, NMELS = 24000, 240, 1024, 64
+CLIP_S = 10
+C = 4
+L = SR * CLIP_S
+T = 1 + L // HOP
+ALGO_BYTES_PER_CLIP = C * L * 4 + (C + 3) * T * NMELS * 4      # 5,633,792
+CFG = {'data': {'sample_rate': SR, 'nfft': NFFT, 'hoplen': HOP, 'n_mels': NMELS,
+                'window': 'hann', 'audio_feature': 'logmelIV'}}
+METRIC = 'audio-seconds/sec (log-mel+IV, 4ch 24 kHz)'
+UNIT = 'audio-s/s'
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.thread = None
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([v.strip() for v in line.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=10)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_port_throughput(batch, min_seconds, max_calls, threads):
+    """The reference's CPU path (oracle/torch_port.py: same torch.stft / matmul calls as the
+    reference makes through torchaudio) on the host cores.  Returns (audio-s/s, calls, seconds)."""
+    import torch
+    from oracle import torch_port
+    from pseldnets_b200 import filterbank as fbk
+    torch.set_num_threads(threads)
+    win = fbk.make_window('hann', NFFT)
+    fb = fbk.melscale_fbanks_htk_slaney(NFFT // 2 + 1, 20, SR / 2, NMELS, SR)
+    g = torch.Generator().manual_seed(1234)
+    x = 0.1 * torch.randn(batch, C, L, generator=g)
+    torch_port.logmel_iv(x, win, fb, NFFT, HOP)          # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_calls and (time.perf_counter() - t_start < min_seconds or len(times) < 3):
+        t0 = time.perf_counter()
+        torch_port.logmel_iv(x, win, fb, NFFT, HOP)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return batch * CLIP_S / med, len(times), sum(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (torch port of
+    feature.py -- the Python reference tree cannot travel to the GPU box), all host threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_port
+    from pseldnets_b200 import filterbank as fbk
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sample_b = 8                                           # bounded sample of the 64-clip batch
+    win = fbk.make_window('hann', NFFT)
+    fb = fbk.melscale_fbanks_htk_slaney(NFFT // 2 + 1, 20, SR / 2, NMELS, SR)
+    g = torch.Generator().manual_seed(1234)
+    x = 0.1 * torch.randn(sample_b, C, L, generator=g)
+    for _ in range(args.warmup):
+        torch_port.logmel_iv(x, win, fb, NFFT, HOP)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        torch_port.logmel_iv(x, win, fb, NFFT, HOP)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample_b * CLIP_S / dt
+    sample = '%d of 64 clips per step (10 s, 4 ch, 24 kHz), torch CPU fp32' % sample_b
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'cfg2 FOA log-mel+IV, 10 s x 4 ch @ 24 kHz clips; CPU sample of %d clips/step' % sample_b,
+                   'n_fft': NFFT, 'hop': HOP, 'n_mels': NMELS},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import pseldnets_b200 as pb
+    from pseldnets_b200 import _abi
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the hot path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.batch
+    ext = pb.get_afextractor(CFG).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # synthetic clips, resident in HBM (each rank its own shard of the global batch: weak scaling)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = 0.1 * torch.randn(B, C, L, device=dev, generator=g)
+    y = None
+    for _ in range(max(args.warmup, 3)):
+        y = ext(x)
+    barrier()
+
+    # ---- timed region: K steps, device timing on the launching (current) stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _abi.lib().seld_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        y = ext(x)
+        ev[i + 1].record()
+    barrier()
+    launches = _abi.lib().seld_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with HOST buffers (H2D + kernel + D2H per step)
+    xh = x.cpu().pin_memory()
+    yh = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+    xd = torch.empty_like(x)
+    for _ in range(2):
+        xd.copy_(xh, non_blocking=True); yh.copy_(ext(xd), non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        xd.copy_(xh, non_blocking=True)
+        yh.copy_(ext(xd), non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # result check only: NCCL gather of per-clip checksums (16 B / clip), after timing
+        chk = torch.stack([y.double().sum(dim=(1, 2, 3)), (y.double() ** 2).sum(dim=(1, 2, 3))], dim=1)
+        allchk = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        finite = all(bool(torch.isfinite(c).all()) for c in allchk)
+    else:
+        finite = bool(torch.isfinite(y).all())
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        audio_s = world * B * CLIP_S
+        value = audio_s * args.steps / (total_ms * 1e-3)
+        launch_ms = statistics.mean(per_launch_ms)
+        achieved = B * ALGO_BYTES_PER_CLIP / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get('foa_features_kernel_bytes_per_launch')
+            except Exception:
+                traffic = None
+        cpu_threads = os.cpu_count() or 1
+        cpu_val, cpu_calls, cpu_secs = cpu_port_throughput(8, args.cpu_seconds, 200, cpu_threads)
+        out = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'cfg2: FOA log-mel+IV, batch %d x 10 s x 4 ch @ 24 kHz per GPU -> (%d,7,1001,64)' % (B, B),
+                       'n_fft': NFFT, 'hop': HOP, 'n_mels': NMELS, 'per_gpu_batch': B, 'global_batch': B * world,
+                       'sharding': 'by clip, no collective on the data path',
+                       'l2': 'inputs 245.8 MB + outputs 114.8 MB per step exceed the 126 MB L2 (no flush needed)'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'foa_features_kernel<true>',
+                         'algorithmic_bytes_per_launch': B * ALGO_BYTES_PER_CLIP, 'launch_ms': launch_ms},
+            'cpu_baseline': {'value': cpu_val, 'unit': UNIT, 'cores': cpu_threads, 'kind': 'port',
+                             'sample': '%d calls of 8 clips (10 s, 4 ch, 24 kHz) in %.1f s, torch CPU fp32 port of feature.py' % (cpu_calls, cpu_secs)},
+            'e2e': {'value': audio_s * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': B * C * L * 4, 'd2h_bytes_per_step': B * (C + 3) * T * NMELS * 4,
+                    'steps': e2e_steps, 'path': 'pinned host -> H2D -> LogmelIV_Extractor.forward -> D2H pinned host'},
+            'gpu_launches': int(launches), 'clocks': clocks, 'outputs_finite': finite,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='clips per GPU per step (cfg2: 64)')
+    ap.add_argument('--cpu-seconds', type=float, default=10.0, help='bound on the cpu_baseline sample')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,67 @@
+/* seldfeat.h -- C ABI of the B200-native SELD feature front-end (libseldfeat.so).
+ *
+ * Drop-in boundary for the hot path of Jinbo-Hu/PSELDNets: the waveform -> feature-map
+ * extractors of /root/reference/src/utils/feature.py.  The reference has no FFI (it is pure
+ * Python on torchaudio); these are the entry points a binding for that path would call.  Every
+ * function cites the reference interface it stands in for.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); device pointers are owned by the
+ * caller (e.g. the PyTorch allocator); compute entry points never allocate, never synchronise
+ * and never throw -- they enqueue on `stream` (a cudaStream_t passed as void*) and return 0 or a
+ * negative SELD_E* code.  All tensors are fp32.
+ */
+#ifndef SELDFEAT_H_
+#define SELDFEAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SELD_OK 0
+#define SELD_EINVAL (-1)      /* bad argument (null pointer, non-positive size, C < 4 for IV ...) */
+#define SELD_EUNSUPPORTED (-2) /* configuration outside what the kernels implement (n_fft != 1024, hop too large) */
+#define SELD_ESHORT (-3)      /* clip too short for reflect padding: torch.stft needs n_fft/2 < L */
+#define SELD_ECUDA (-4)       /* a CUDA runtime call failed; see seld_last_cuda_error() */
+#define SELD_ENOMEM (-5)
+
+typedef struct seld_plan seld_plan;
+
+/* Build the constant tables of one extractor configuration on `device`.
+ * Stands in for LogmelIV_Extractor.__init__ / Logmel_Extractor.__init__ (feature.py:21-37,
+ * 60-75): `window_host` is the (n_fft,) analysis window the reference keeps as
+ * `stft_extractor.window`, `fb_host` the (n_fft/2+1, n_mels) row-major mel bank it keeps as
+ * `mel_scale.fb`; amin is AmplitudeToDB's clamp (1e-10), eps the intensity-vector epsilon
+ * (feature.py:8).  Allocates device memory; not on the per-step path. */
+int seld_plan_create(seld_plan** plan, int device, const float* window_host, const float* fb_host,
+                     int n_fft, int hop, int n_mels, float amin, float eps);
+void seld_plan_destroy(seld_plan* plan);
+
+/* Frames produced for a clip of L samples: 1 + L / hop (torch.stft, center=True). */
+int64_t seld_num_frames(const seld_plan* plan, int64_t L);
+
+/* LogmelIV_Extractor.forward (feature.py:39-56): x (B, C>=4, L) device fp32 with element
+ * strides (stride_b, stride_c, 1) -> out (B, C+3, T, n_mels) contiguous device fp32:
+ * C log-mel maps followed by the 3 mel-projected normalised intensity-vector maps of channels
+ * 1..3 against channel 0 (intensityvector, feature.py:93-117). */
+int seld_logmel_iv_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
+                       int64_t stride_b, int64_t stride_c, float* out, void* stream);
+
+/* Logmel_Extractor.forward (feature.py:76-91): x (B, C>=1, L) -> out (B, C, T, n_mels). */
+int seld_logmel_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
+                    int64_t stride_b, int64_t stride_c, float* out, void* stream);
+
+/* Kernels enqueued by this library since load (all entry points, all plans). */
+uint64_t seld_launch_count(void);
+/* cudaError_t of the most recent failing runtime call on this thread (0 if none). */
+int seld_last_cuda_error(void);
+const char* seld_strerror(int code);
+/* "seldfeat <version> sm_100a" */
+const char* seld_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELDFEAT_H_ */

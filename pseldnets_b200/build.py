@@ -1,0 +1,43 @@
+"""Build libseldfeat.so (the CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+    python -m pseldnets_b200.build          # rebuilds pseldnets_b200/libseldfeat.so
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libseldfeat.so')
+SOURCES = ['seld_foa.cu', 'seld_abi.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
+              '-Xcompiler', '-fPIC', '-shared']
+
+
+def _newest_source_mtime():
+    m = 0.0
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), 'include')):
+        for fn in os.listdir(root):
+            m = max(m, os.path.getmtime(os.path.join(root, fn)))
+    return m
+
+
+def build(force=False, verbose=False):
+    """Compile if the library is missing or older than any source.  Returns the .so path."""
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+        return LIB
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+          ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force=True, verbose='-v' in sys.argv))

@@ -1,0 +1,170 @@
+// C-ABI layer of libseldfeat.so: plan construction (host-side table building, device upload) and
+// the per-call argument checks + launches.  See include/seldfeat.h for the contract.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "../../include/seldfeat.h"
+#include "seld_plan.h"
+
+struct seld_plan {
+    seld::PlanDev dev;
+    int device;
+    int sm_count;
+    int n_fft;
+    size_t smem_optin;
+    void* blob;            // one device allocation holding every table
+};
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local int g_last_cuda = 0;
+
+static int cuda_fail(cudaError_t e) {
+    g_last_cuda = (int)e;
+    return SELD_ECUDA;
+}
+
+extern "C" int seld_plan_create(seld_plan** out, int device, const float* window_host, const float* fb_host,
+                                int n_fft, int hop, int n_mels, float amin, float eps) {
+    if (!out || !window_host || !fb_host || hop <= 0 || n_mels <= 0) return SELD_EINVAL;
+    if (n_fft != 1024) return SELD_EUNSUPPORTED;     // the warp-wide transform is 32 x 32
+    const int F = n_fft / 2 + 1;
+
+    // ---- band-sparse view of the mel bank: per band the [lo, lo+cnt) support and its weights
+    std::vector<int> blo(n_mels), bcnt(n_mels), boff(n_mels);
+    std::vector<float> wt;
+    for (int m = 0; m < n_mels; ++m) {
+        int lo = F, hi = -1;
+        for (int k = 0; k < F; ++k)
+            if (fb_host[(size_t)k * n_mels + m] != 0.0f) { if (k < lo) lo = k; hi = k; }
+        blo[m] = hi < 0 ? 0 : lo;
+        bcnt[m] = hi < 0 ? 0 : hi - lo + 1;
+        boff[m] = (int)wt.size();
+        for (int k = blo[m]; k < blo[m] + bcnt[m]; ++k) wt.push_back(fb_host[(size_t)k * n_mels + m]);
+    }
+    while (wt.size() % 4) wt.push_back(0.0f);
+    if (wt.empty()) wt.assign(4, 0.0f);
+    const int n_mels_pad = (n_mels + 3) & ~3;
+
+    // ---- twiddles W1024^(ka*j), window * 0.5
+    std::vector<float> tw(2 * 1024), win(n_fft);
+    for (int ka = 0; ka < 32; ++ka)
+        for (int j = 0; j < 32; ++j) {
+            const double ang = 2.0 * M_PI * (double)((ka * j) % 1024) / 1024.0;
+            tw[2 * (ka * 32 + j)] = (float)cos(ang);
+            tw[2 * (ka * 32 + j) + 1] = (float)(-sin(ang));
+        }
+    for (int i = 0; i < n_fft; ++i) win[i] = 0.5f * window_host[i];
+
+    seld_plan* p = new (std::nothrow) seld_plan();
+    if (!p) return SELD_ENOMEM;
+    memset(p, 0, sizeof(*p));
+    p->device = device; p->n_fft = n_fft;
+
+    int prev = 0;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e == cudaSuccess) e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e); }
+    int smem_optin = 0;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    p->smem_optin = (size_t)smem_optin;
+
+    const size_t b_tw = tw.size() * 4, b_win = win.size() * 4, b_wt = wt.size() * 4, b_i = (size_t)n_mels_pad * 4;
+    const size_t total = b_tw + b_win + b_wt + 3 * b_i;
+    e = cudaMalloc(&p->blob, total);
+    if (e != cudaSuccess) { cudaSetDevice(prev); delete p; return cuda_fail(e); }
+    std::vector<unsigned char> host(total, 0);
+    size_t o = 0;
+    memcpy(&host[o], tw.data(), b_tw); const size_t o_tw = o; o += b_tw;
+    memcpy(&host[o], win.data(), b_win); const size_t o_win = o; o += b_win;
+    memcpy(&host[o], wt.data(), b_wt); const size_t o_wt = o; o += b_wt;
+    memcpy(&host[o], blo.data(), n_mels * 4); const size_t o_lo = o; o += b_i;
+    memcpy(&host[o], bcnt.data(), n_mels * 4); const size_t o_cnt = o; o += b_i;
+    memcpy(&host[o], boff.data(), n_mels * 4); const size_t o_off = o; o += b_i;
+    e = cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { cudaFree(p->blob); delete p; return cuda_fail(e); }
+
+    unsigned char* d = (unsigned char*)p->blob;
+    p->dev.tw = (const float2*)(d + o_tw);
+    p->dev.win = (const float*)(d + o_win);
+    p->dev.wt = (const float*)(d + o_wt);
+    p->dev.blo = (const int*)(d + o_lo);
+    p->dev.bcnt = (const int*)(d + o_cnt);
+    p->dev.boff = (const int*)(d + o_off);
+    p->dev.nnz_pad = (int)wt.size();
+    p->dev.n_mels = n_mels; p->dev.n_mels_pad = n_mels_pad;
+    p->dev.hop = hop; p->dev.amin = amin; p->dev.eps = eps;
+
+    // the tile (frames_per_tile-1)*hop + n_fft samples x 4 channels must fit next to the tables
+    const int span = (((seld::foa_frames_per_tile() - 1) * hop + n_fft) + 3) & ~3;
+    if (seld::foa_smem_bytes(p->dev, span) > p->smem_optin) { seld_plan_destroy(p); return SELD_EUNSUPPORTED; }
+    *out = p;
+    return SELD_OK;
+}
+
+extern "C" void seld_plan_destroy(seld_plan* p) {
+    if (!p) return;
+    if (p->blob) cudaFree(p->blob);
+    delete p;
+}
+
+extern "C" int64_t seld_num_frames(const seld_plan* p, int64_t L) {
+    if (!p || L < 0) return SELD_EINVAL;
+    return 1 + L / p->dev.hop;
+}
+
+static int run_foa(const seld_plan* p, bool iv, const float* x, int64_t B, int C, int64_t L,
+                   int64_t stride_b, int64_t stride_c, float* out, void* stream) {
+    if (!p || !x || !out || B < 0 || C < 1 || L < 1) return SELD_EINVAL;
+    if (iv && C < 4) return SELD_EINVAL;               // intensityvector indexes channels 0..3
+    if (L <= p->n_fft / 2) return SELD_ESHORT;         // reflect padding needs pad < L (torch.stft)
+    if (B == 0) return SELD_OK;
+    const int64_t T = 1 + L / p->dev.hop;
+    const int fpt = seld::foa_frames_per_tile();
+    const int64_t tiles_per_clip = (T + fpt - 1) / fpt;
+    if (B * tiles_per_clip > INT32_MAX || T > INT32_MAX) return SELD_EUNSUPPORTED;
+    seld::FoaArgs a;
+    a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
+    a.B = (int)B; a.C = C; a.Cout = C + (iv ? 3 : 0); a.T = (int)T;
+    a.tiles_per_clip = (int)tiles_per_clip; a.n_tiles = (int)(B * tiles_per_clip);
+    a.span = (((fpt - 1) * p->dev.hop + p->n_fft) + 3) & ~3;
+    a.vec_ok = (((uintptr_t)x & 15) == 0) && (stride_b % 4 == 0) && (stride_c % 4 == 0) && (p->dev.hop % 4 == 0);
+    cudaError_t e = seld::foa_launch(iv, a, p->dev, p->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
+extern "C" int seld_logmel_iv_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,
+                                  int64_t stride_b, int64_t stride_c, float* out, void* stream) {
+    return run_foa(p, true, x, B, C, L, stride_b, stride_c, out, stream);
+}
+
+extern "C" int seld_logmel_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,
+                               int64_t stride_b, int64_t stride_c, float* out, void* stream) {
+    return run_foa(p, false, x, B, C, L, stride_b, stride_c, out, stream);
+}
+
+extern "C" uint64_t seld_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int seld_last_cuda_error(void) { return g_last_cuda; }
+
+extern "C" const char* seld_strerror(int code) {
+    switch (code) {
+        case SELD_OK: return "ok";
+        case SELD_EINVAL: return "invalid argument";
+        case SELD_EUNSUPPORTED: return "unsupported configuration (n_fft must be 1024; tile must fit shared memory)";
+        case SELD_ESHORT: return "clip too short: reflect padding needs n_fft/2 < L";
+        case SELD_ECUDA: return "CUDA runtime error";
+        case SELD_ENOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char* seld_version(void) { return "seldfeat 0.1 sm_100a"; }

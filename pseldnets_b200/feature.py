@@ -1,0 +1,126 @@
+"""Drop-in extractor modules: same names, constructor and forward contract as the reference's
+/root/reference/src/utils/feature.py, with the arithmetic done by the fused sm_100a kernels of
+libseldfeat.so instead of ~45 torchaudio / ATen / cuFFT / cuBLAS launches.
+
+    LogmelIV_Extractor(cfg)(x)  x (B, C>=4, L) fp32 cuda -> (B, C+3, 1+L//hop, n_mels)   feature.py:20-56
+    Logmel_Extractor(cfg)(x)    x (B, C,    L) fp32 cuda -> (B, C,   1+L//hop, n_mels)   feature.py:59-91
+
+State: no parameters; the same two persistent buffers under the same names the reference's
+checkpoints contain (`stft_extractor.window`, `mel_scale.fb`).  The kernels take their tables from
+those buffers, so a loaded state_dict is honoured.  Output is a fresh tensor each call (callers
+mutate it in place: accdoa.py:224-227, specaug.py:55-57).  Runs on the current CUDA stream; no
+backward (the reference's input never requires grad).
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .filterbank import make_window, melscale_fbanks_htk_slaney, window_fn_dict  # noqa: F401
+
+eps = torch.finfo(torch.float32).eps  # feature.py:8
+AMIN = 1e-10                          # torchaudio AmplitudeToDB
+
+
+class _Buffer(nn.Module):
+    """Holder giving a buffer the attribute path it has in the reference's state_dict."""
+
+    def __init__(self, name, value):
+        super().__init__()
+        self.register_buffer(name, value)
+
+
+class _Plan:
+    """Owns one seld_plan (device tables) for a (device, buffer contents) pair."""
+
+    def __init__(self, device_index, window, fb, n_fft, hop, n_mels):
+        w = window.detach().to('cpu', torch.float32).contiguous()
+        f = fb.detach().to('cpu', torch.float32).contiguous()
+        handle = ctypes.c_void_p()
+        code = _abi.lib().seld_plan_create(
+            ctypes.byref(handle), device_index,
+            ctypes.cast(w.data_ptr(), ctypes.POINTER(ctypes.c_float)),
+            ctypes.cast(f.data_ptr(), ctypes.POINTER(ctypes.c_float)),
+            n_fft, hop, n_mels, AMIN, eps)
+        _abi.check(code, 'seld_plan_create')
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                _abi.lib().seld_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _ExtractorBase(nn.Module):
+    _entry = None       # C-ABI symbol
+    _extra_ch = 0
+
+    def __init__(self, cfg):
+        super().__init__()
+        data = cfg['data']
+        assert data['window'] in window_fn_dict.keys(), \
+            "window must be in {}, but got {}".format(window_fn_dict.keys(), data['window'])
+        self.n_fft = int(data['nfft'])
+        self.hop = int(data['hoplen'])
+        self.n_mels = int(data['n_mels'])
+        self.sample_rate = data['sample_rate']
+        self.stft_extractor = _Buffer('window', make_window(data['window'], self.n_fft))
+        self.mel_scale = _Buffer('fb', melscale_fbanks_htk_slaney(
+            self.n_fft // 2 + 1, 20, self.sample_rate / 2, self.n_mels, self.sample_rate))
+        self._plans = {}
+
+    def _plan(self, device):
+        win, fb = self.stft_extractor.window, self.mel_scale.fb
+        key = (device.index, win.data_ptr(), win._version, fb.data_ptr(), fb._version)
+        plan = self._plans.get(device.index)
+        if plan is None or plan[0] != key:
+            plan = (key, _Plan(device.index, win, fb, self.n_fft, self.hop, self.n_mels))
+            self._plans[device.index] = plan
+        return plan[1]
+
+    def forward(self, x):
+        """
+        input:
+            (batch_size, channels, data_length)
+        output:
+            (batch_size, channels(+3), time_steps, mel_bins)
+        """
+        if x.ndim != 3:
+            raise ValueError("x shape must be (batch_size, num_channels, data_length)\n \
+                            Now it is {}".format(x.shape))
+        if not x.is_cuda:
+            raise RuntimeError('pseldnets_b200 extractors run on CUDA tensors only (no CPU path); '
+                               'got a tensor on %s' % x.device)
+        if x.dtype != torch.float32:
+            raise TypeError('expected float32 waveform, got %s' % x.dtype)
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        B, C, L = x.shape
+        dev = x.device
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        plan = self._plan(dev)
+        T = 1 + L // self.hop
+        out = torch.empty((B, C + self._extra_ch, T, self.n_mels), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        fn = getattr(_abi.lib(), self._entry)
+        code = fn(plan.handle, x.data_ptr(), B, C, L, x.stride(0), x.stride(1), out.data_ptr(), stream)
+        _abi.check(code, self._entry)
+        return out
+
+
+class LogmelIV_Extractor(_ExtractorBase):
+    """log-mel of every channel + mel-projected normalised intensity vector of channels 1..3
+    against channel 0 (FOA: W, Y, Z, X).  feature.py:20-56, 93-117."""
+    _entry = 'seld_logmel_iv_f32'
+    _extra_ch = 3
+
+
+class Logmel_Extractor(_ExtractorBase):
+    """log-mel of every channel.  feature.py:59-91."""
+    _entry = 'seld_logmel_f32'
+    _extra_ch = 0

@@ -1,0 +1,117 @@
+"""CPU: host-side logic of the drop-in (constructor, buffers, errors, factory), the C-ABI
+library's exported symbols, and the host model of the warp FFT index algebra."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, make_cfg
+import pseldnets_b200 as pb
+from pseldnets_b200 import _abi, filterbank as fbk
+
+
+def test_buffers_match_reference(golden_small):
+    g, _ = golden_small
+    ext = pb.LogmelIV_Extractor(make_cfg())
+    sd = ext.state_dict()
+    assert repr(sorted(sd.keys())) == str(g['buffers/keys'])
+    assert np.array_equal(sd['stft_extractor.window'].numpy(), g['buffers/window'])
+    assert np.array_equal(sd['mel_scale.fb'].numpy(), g['buffers/fb_24k'])
+    ext32 = pb.Logmel_Extractor(make_cfg(32000, 320, feat='logmel'))
+    assert np.array_equal(ext32.mel_scale.fb.numpy(), g['buffers/fb_32k'])
+    assert len(list(ext.parameters())) == 0
+
+
+def test_state_dict_roundtrip_strict():
+    a = pb.LogmelIV_Extractor(make_cfg())
+    b = pb.LogmelIV_Extractor(make_cfg(window='hamming'))
+    b.load_state_dict(a.state_dict(), strict=True)
+    assert torch.equal(b.stft_extractor.window, a.stft_extractor.window)
+
+
+def test_ctor_and_forward_errors():
+    with pytest.raises(AssertionError):
+        pb.LogmelIV_Extractor(make_cfg(window='kaiser'))
+    ext = pb.LogmelIV_Extractor(make_cfg())
+    with pytest.raises(ValueError):
+        ext(torch.zeros(4, 2400))
+    with pytest.raises(RuntimeError):          # no CPU path: fail loudly
+        ext(torch.zeros(1, 4, 2400))
+
+
+def test_factory():
+    assert isinstance(pb.get_afextractor(make_cfg(feat='logmelIV')), pb.LogmelIV_Extractor)
+    assert isinstance(pb.get_afextractor(make_cfg(feat='logmel')), pb.Logmel_Extractor)
+    assert pb.get_afextractor(make_cfg(feat='salsalite')) is None
+
+
+def test_windows_and_banks():
+    for name in ('hann', 'hamming', 'blackman', 'bartlett'):
+        w = fbk.make_window(name, 1024)
+        assert w.shape == (1024,) and w.dtype == torch.float32
+    fb = fbk.melscale_fbanks_htk_slaney(513, 20, 12000, 64, 24000)
+    assert fb.shape == (513, 64) and int((fb != 0).sum()) == 998
+    assert int(((fb != 0).sum(dim=1)).max()) <= 2             # every bin feeds <= 2 bands
+    bank = fbk.librosa_mel_bank(24000, 1024, 64)
+    assert bank.shape == (513, 64) and bank.dtype == torch.float32
+    try:
+        import torchaudio
+    except Exception:
+        return
+    ref = torchaudio.functional.melscale_fbanks(513, 20, 12000, 64, 24000, norm='slaney', mel_scale='htk')
+    assert torch.equal(fb, ref)
+    ref2 = torchaudio.functional.melscale_fbanks(513, 0, 12000, 64, 24000, norm='slaney', mel_scale='slaney')
+    assert (bank - ref2).abs().max() < 1e-7
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'seldfeat.h')).read()
+    declared = set(re.findall(r'\b(seld_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), 'libseldfeat.so does not export %s' % name
+    assert declared == set(_abi.SIGNATURES), declared ^ set(_abi.SIGNATURES)
+    assert _abi.lib().seld_version().decode().endswith('sm_100a')
+    assert _abi.lib().seld_strerror(_abi.SELD_ESHORT).decode().startswith('clip too short')
+
+
+def test_abi_argument_checks_without_gpu():
+    """Entry points validate before touching CUDA: callable on a CPU-only host."""
+    l = _abi.lib()
+    assert l.seld_logmel_iv_f32(None, None, 1, 4, 2400, 9600, 2400, None, None) == _abi.SELD_EINVAL
+    h = ctypes.c_void_p()
+    w = np.ones(1024, np.float32)
+    fb = np.ones((513, 64), np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    assert l.seld_plan_create(ctypes.byref(h), 0, w.ctypes.data_as(fp), fb.ctypes.data_as(fp),
+                              512, 240, 64, 1e-10, 1e-7) == _abi.SELD_EUNSUPPORTED
+    assert l.seld_plan_create(ctypes.byref(h), 0, w.ctypes.data_as(fp), fb.ctypes.data_as(fp),
+                              1024, 0, 64, 1e-10, 1e-7) == _abi.SELD_EINVAL
+
+
+def test_host_model_of_warp_fft(tmp_path):
+    """The kernel's 32x32 index algebra (same fft32.cuh, compiled for the host) equals rfft."""
+    so_path = str(tmp_path / 'fft_model.so')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-o', so_path,
+                           os.path.join(ROOT, 'tests', 'host', 'fft_model.cpp')])
+    lib = ctypes.CDLL(so_path)
+    fp = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(0)
+    r = rng.standard_normal(32).astype(np.float32)
+    i = rng.standard_normal(32).astype(np.float32)
+    ref = np.fft.fft(r.astype(np.float64) + 1j * i)
+    lib.model_fft32(r.ctypes.data_as(fp), i.ctypes.data_as(fp))
+    assert np.abs((r + 1j * i) - ref).max() < 1e-6 * np.abs(ref).max()
+    a = rng.standard_normal(1024).astype(np.float32)
+    b = rng.standard_normal(1024).astype(np.float32)
+    A = np.zeros(1026, np.float32)
+    Bv = np.zeros(1026, np.float32)
+    lib.model_fft1024_pair(a.ctypes.data_as(fp), b.ctypes.data_as(fp), A.ctypes.data_as(fp), Bv.ctypes.data_as(fp))
+    Ar, Br = np.fft.rfft(2 * a.astype(np.float64)), np.fft.rfft(2 * b.astype(np.float64))
+    assert np.abs((A[0::2] + 1j * A[1::2]) - Ar).max() < 1e-6 * np.abs(Ar).max()
+    assert np.abs((Bv[0::2] + 1j * Bv[1::2]) - Br).max() < 1e-6 * np.abs(Br).max()

@@ -1,0 +1,101 @@
+"""CPU: pin the oracle (numpy restatement + torch port) to golden vectors made from the real
+reference (tests/golden/make_golden.py).  The reference ships no vectors of its own."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_blocks_close, block_err, golden_input
+from oracle import seld_oracle as so
+from oracle import torch_port as tp
+from pseldnets_b200 import filterbank as fbk
+
+
+def _tables(sr, win):
+    w = fbk.make_window(win, 1024)
+    fb = fbk.melscale_fbanks_htk_slaney(513, 20, sr / 2, 64, sr)
+    return w, fb
+
+
+def test_synth_inputs_are_reproducible(golden_small):
+    g, meta = golden_small
+    for name, kind, sr, hop, win, recipe in meta:
+        assert np.array_equal(golden_input(recipe), g[name + '/x']), name
+
+
+def test_numpy_oracle_fp64_is_the_reference_algorithm(golden_small):
+    """fp64 evaluation agrees with the reference module run in fp64 to ~1e-13: same algorithm."""
+    g, meta = golden_small
+    for name, kind, sr, hop, win, recipe in meta:
+        w, fb = _tables(sr, win)
+        f = so.logmel_iv if kind == 'logmelIV' else so.logmel
+        y = f(g[name + '/x'], w.numpy(), fb.numpy(), 1024, hop, np.float64)
+        C = g[name + '/x'].shape[1]
+        assert_blocks_close(y, g[name + '/y64'], C, tol=1e-11, what=name)
+
+
+def test_numpy_oracle_fp32_matches_reference_fp32(golden_small):
+    g, meta = golden_small
+    for name, kind, sr, hop, win, recipe in meta:
+        w, fb = _tables(sr, win)
+        f = so.logmel_iv if kind == 'logmelIV' else so.logmel
+        y = f(g[name + '/x'], w.numpy(), fb.numpy(), 1024, hop, np.float32)
+        assert y.dtype == np.float32
+        C = g[name + '/x'].shape[1]
+        assert_blocks_close(y, g[name + '/y32'], C, tol=1e-5, what=name)
+
+
+def test_torch_port_matches_reference_fp32(golden_small):
+    """Same library calls as the reference -> same numbers up to the host's FFT/BLAS rounding."""
+    g, meta = golden_small
+    for name, kind, sr, hop, win, recipe in meta:
+        w, fb = _tables(sr, win)
+        f = tp.logmel_iv if kind == 'logmelIV' else tp.logmel
+        y = f(torch.from_numpy(g[name + '/x']), w, fb, 1024, hop).numpy()
+        C = g[name + '/x'].shape[1]
+        assert_blocks_close(y, g[name + '/y32'], C, tol=1e-5, what=name)
+
+
+def test_oracle_cfg1_full_size(golden_cfg1):
+    from oracle import synth
+    g = golden_cfg1
+    x = synth.white(1234, 1, 4, 240000)
+    w, fb = _tables(24000, 'hann')
+    y = so.logmel_iv(x, w.numpy(), fb.numpy(), 1024, 240, np.float32)
+    assert tuple(y.shape) == tuple(g['shape'])
+    assert_blocks_close(y[:, :, g['frames']], g['y32'], 4, tol=1e-5, what='cfg1')
+    y64 = so.logmel_iv(x, w.numpy(), fb.numpy(), 1024, 240, np.float64)
+    np.testing.assert_allclose(y64.sum(axis=(2, 3)), g['sum64'], rtol=1e-9)
+    np.testing.assert_allclose((y64 ** 2).sum(axis=(2, 3)), g['sumsq64'], rtol=1e-9)
+
+
+def test_oracle_edge_semantics():
+    w, fb = _tables(24000, 'hann')
+    z = np.zeros((1, 4, 2400), np.float32)
+    y = so.logmel_iv(z, w.numpy(), fb.numpy(), 1024, 240)
+    # silence -> amin clamp (-100 dB up to fp32 log10 rounding) and exactly zero IV
+    assert np.abs(y[:, :4] + 100.0).max() < 1e-4 and np.all(y[:, 4:] == 0.0)
+    with pytest.raises(ValueError):
+        so.logmel_iv(np.zeros((4, 2400), np.float32), w.numpy(), fb.numpy(), 1024, 240)
+    with pytest.raises(ValueError):
+        tp.logmel(torch.zeros(4, 2400), w, fb, 1024, 240)
+
+
+def test_mic_oracle_self_consistency():
+    """MIC restatement ("parity unpinned": librosa is not installable): fp32 vs fp64 evaluation,
+    shapes, GCC of a pure delay peaks at that lag, top_db floor."""
+    from oracle import synth
+    sr, hop = 24000, 240
+    w = fbk.make_window('hann', 1024).numpy()
+    bank = fbk.librosa_mel_bank(sr, 1024, 64).numpy()
+    x = synth.white(5, 1, 1, 4800 + 8)[0, 0]
+    d = 5
+    mics = np.stack([x[8:8 + 4800], x[8 - d:8 - d + 4800], x[8:8 + 4800], x[8 - 2:8 - 2 + 4800]])[None]
+    y32 = so.logmel_gcc(mics, w, bank, 1024, hop, dtype=np.float32)
+    y64 = so.logmel_gcc(mics, w, bank, 1024, hop, dtype=np.float64)
+    assert y32.shape == (1, 10, 20, 64)
+    assert block_err(y32, y64, slice(0, 4)) < 1e-5
+    assert np.abs(y32[:, 4:] - y64[:, 4:]).max() < 1e-4
+    # pair (0,1): mic 1 lags mic 0 by d samples -> peak at lag +d -> column 32 + d
+    assert int(np.argmax(y64[0, 4, 10])) == 32 + d
+    assert int(np.argmax(y64[0, 5, 10])) == 32          # identical channels: lag 0
+    assert y64[0, :4].min() >= y64[0, :4].max() - 80.0 - 1e-9

@@ -1,0 +1,196 @@
+"""GPU: the CUDA path (through the nn.Module -> ctypes -> C ABI -> sm_100a kernels) against the
+golden vectors of the real reference, against the CPU oracle on seeded inputs, and -- at
+BASELINE sizes -- through size-independent properties.  Tolerance (north_star): log-mel and IV
+within 1e-4 of the block's max |ref| in fp32."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import RTOL_BLOCK, assert_blocks_close, block_err, golden_input, make_cfg
+import pseldnets_b200 as pb
+from pseldnets_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _ext(kind, sr, hop, win):
+    cls = pb.LogmelIV_Extractor if kind == 'logmelIV' else pb.Logmel_Extractor
+    return cls(make_cfg(sr, hop, win, kind)).cuda()
+
+
+def _run(ext, x):
+    y = ext(torch.from_numpy(np.ascontiguousarray(x)).cuda())
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+def test_extension_is_loaded_and_launches():
+    before = _abi.lib().seld_launch_count()
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    y = ext(torch.zeros(1, 4, 2400, device='cuda'))
+    torch.cuda.synchronize()
+    assert _abi.lib().seld_launch_count() == before + 1
+    assert y.shape == (1, 7, 11, 64) and y.is_contiguous() and y.dtype == torch.float32
+
+
+def test_golden_small_fixtures(golden_small):
+    g, meta = golden_small
+    for name, kind, sr, hop, win, recipe in meta:
+        x = g[name + '/x']
+        y = _run(_ext(kind, sr, hop, win), x)
+        C = x.shape[1]
+        assert_blocks_close(y, g[name + '/y32'], C, what=name + ' vs reference fp32')
+        assert_blocks_close(y, g[name + '/y64'], C, what=name + ' vs reference fp64')
+
+
+def test_silence_is_exact():
+    y = _run(_ext('logmelIV', 24000, 240, 'hann'), np.zeros((2, 4, 4800), np.float32))
+    assert np.abs(y[:, :4] + 100.0).max() < 1e-4
+    assert np.all(y[:, 4:] == 0.0)
+
+
+def test_cfg1_full_clip_against_reference(golden_cfg1):
+    from oracle import synth
+    g = golden_cfg1
+    x = synth.white(1234, 1, 4, 240000)
+    y = _run(_ext('logmelIV', 24000, 240, 'hann'), x)
+    assert tuple(y.shape) == tuple(g['shape']) == (1, 7, 1001, 64)
+    assert_blocks_close(y[:, :, g['frames']], g['y32'], 4, what='cfg1 frames vs reference fp32')
+    assert_blocks_close(y[:, :, g['frames']], g['y64'], 4, what='cfg1 frames vs reference fp64')
+    # whole-map digests of the fp64 reference: every frame is covered, not just the subsample
+    s = y.astype(np.float64).sum(axis=(2, 3))
+    ss = (y.astype(np.float64) ** 2).sum(axis=(2, 3))
+    np.testing.assert_allclose(s, g['sum64'], rtol=0, atol=1e-4 * g['absmax'] * 1001 * 64 * 0.05)
+    np.testing.assert_allclose(ss, g['sumsq64'], rtol=1e-5)
+
+
+def test_against_oracle_seeded_batch():
+    """Oracle on the same seeded inputs: a batch with distinct clips, both sample rates."""
+    from oracle import seld_oracle as so, synth
+    for sr, hop, L, seed in ((24000, 240, 24000, 101), (32000, 320, 16000, 102)):
+        ext = _ext('logmelIV', sr, hop, 'hann')
+        x = synth.white(seed, 3, 4, L)
+        x[1] = synth.plane_wave_foa(seed + 1, 1, L)[0]
+        y = _run(ext, x)
+        w = ext.stft_extractor.window.cpu().numpy()
+        fb = ext.mel_scale.fb.cpu().numpy()
+        ref = so.logmel_iv(x, w, fb, 1024, hop, np.float64)
+        assert_blocks_close(y, ref, 4, what='sr=%d' % sr)
+
+
+def test_logmel_extractor_channel_counts():
+    from oracle import seld_oracle as so, synth
+    for C in (1, 2, 3, 4, 5, 8):
+        ext = _ext('logmel', 24000, 240, 'hann')
+        x = synth.white(200 + C, 2, C, 3000)
+        y = _run(ext, x)
+        ref = so.logmel(x, ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy(), 1024, 240, np.float64)
+        assert y.shape == (2, C, 13, 64)
+        assert_blocks_close(y, ref, C, what='C=%d' % C)
+
+
+def test_eight_channel_logmel_iv():
+    """C=8 in -> 11 out: 8 log-mel + IV from channels 0-3."""
+    from oracle import seld_oracle as so, synth
+    ext = _ext('logmelIV', 32000, 320, 'hann')
+    x = synth.white(300, 2, 8, 6400)
+    y = _run(ext, x)
+    ref = so.logmel_iv(x, ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy(), 1024, 320, np.float64)
+    assert y.shape == (2, 11, 21, 64)
+    assert_blocks_close(y, ref, 8, what='C=8')
+
+
+def test_noncontiguous_and_strided_inputs():
+    from oracle import synth
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    x = torch.from_numpy(synth.white(400, 3, 6, 4803)).cuda()
+    base = ext(x[:, :4].contiguous())
+    view = x[:, :4]                                  # batch stride 6*L, unaligned rows
+    assert not view.is_contiguous()
+    assert torch.equal(ext(view), base)
+    tm = x.permute(0, 2, 1).contiguous().permute(0, 2, 1)[:, :4]   # time-major storage -> copied
+    assert torch.equal(ext(tm), base)
+    off = torch.from_numpy(synth.white(401, 1, 4, 4801)).cuda()[:, :, 1:]   # misaligned base pointer
+    assert torch.equal(ext(off), ext(off.contiguous()))
+
+
+def test_fresh_output_each_call_and_errors():
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    x = torch.randn(1, 4, 2400, device='cuda') * 0.1
+    a = ext(x)
+    b = ext(x)
+    assert a.data_ptr() != b.data_ptr() and torch.equal(a, b)
+    a.zero_()
+    assert torch.equal(ext(x), b)
+    with pytest.raises(ValueError):
+        ext(torch.zeros(4, 2400, device='cuda'))
+    with pytest.raises(_abi.SeldError):              # reflect pad needs L > 512 (torch.stft raises too)
+        ext(torch.zeros(1, 4, 512, device='cuda'))
+    with pytest.raises(_abi.SeldError):              # intensity vector needs 4 channels
+        ext(torch.zeros(1, 3, 2400, device='cuda'))
+    assert ext(torch.zeros(0, 4, 2400, device='cuda')).shape == (0, 7, 11, 64)
+
+
+def test_loaded_buffers_are_honoured():
+    """A checkpoint's window / fb (state_dict) must drive the kernels, not the constructor's."""
+    from oracle import seld_oracle as so, synth
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    x = synth.white(500, 1, 4, 2400)
+    y0 = _run(ext, x)
+    src = pb.LogmelIV_Extractor(make_cfg(32000, 320, 'blackman'))
+    ext.load_state_dict(src.state_dict())
+    y1 = _run(ext, x)
+    ref = so.logmel_iv(x, src.stft_extractor.window.numpy(), src.mel_scale.fb.numpy(), 1024, 240, np.float64)
+    assert_blocks_close(y1, ref, 4, what='reloaded buffers')
+    assert block_err(y1, y0, slice(0, 4)) > 1e-3
+
+
+def test_dense_filterbank_is_still_correct():
+    """A non-banded fb (every bin feeds every band) takes the generic path of the band table."""
+    from oracle import seld_oracle as so, synth
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    g = torch.Generator().manual_seed(3)
+    ext.mel_scale.fb.copy_((torch.rand(513, 64, generator=g) * 0.01).cuda())
+    x = synth.white(501, 1, 4, 2400)
+    y = _run(ext, x)
+    ref = so.logmel_iv(x, ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy(), 1024, 240, np.float64)
+    assert_blocks_close(y, ref, 4, what='dense fb')
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg2 (B=64 x 10 s): properties that need no oracle at this size."""
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    x = 0.1 * torch.randn(64, 4, 240000, device='cuda', generator=g)
+    y = ext(x)
+    assert y.shape == (64, 7, 1001, 64) and torch.isfinite(y).all()
+    # (1) batch independence / determinism: any clip alone gives the same bits
+    for b in (0, 31, 63):
+        assert torch.equal(ext(x[b:b + 1]), y[b:b + 1])
+    # (2) gain: log-mel shifts by 20*log10(g) dB, IV is scale invariant (eps negligible here)
+    y4 = ext(4.0 * x[:4])
+    shift = 20.0 * np.log10(4.0)
+    assert (y4[:, :4] - y[:4, :4] - shift).abs().max().item() < 1e-4 * y[:4, :4].abs().max().item()
+    assert (y4[:, 4:] - y[:4, 4:]).abs().max().item() < 1e-4 * y[:4, 4:].abs().max().item()
+    # (3) flipping the sign of channel j flips IV_j only; log-mel is unchanged
+    xf = x[:4].clone()
+    xf[:, 2] = -xf[:, 2]
+    yf = ext(xf)
+    assert torch.equal(yf[:, :4], y[:4, :4])
+    assert torch.allclose(yf[:, 5], -y[:4, 5], atol=1e-7) and torch.allclose(yf[:, 4], y[:4, 4], atol=1e-7)
+    # (4) swapping channels 1 and 3 swaps their log-mel and IV maps
+    xs = x[:4][:, [0, 3, 2, 1]].contiguous()
+    ys = ext(xs)
+    tol = 1e-4 * y[:4, 4:].abs().max().item()
+    assert (ys[:, 4] - y[:4, 6]).abs().max().item() < tol and (ys[:, 6] - y[:4, 4]).abs().max().item() < tol
+    assert (ys[:, 1] - y[:4, 3]).abs().max().item() < 1e-4 * y[:4, :4].abs().max().item()
+    # (5) a delay of one hop moves interior frames by one
+    yd = ext(x[:2, :, 240:].contiguous())
+    d = (yd[:, :, 3:900] - y[:2, :, 4:901]).abs()
+    assert d[:, :4].max().item() < 1e-4 * y[:2, :4].abs().max().item()
+    assert d[:, 4:].max().item() < 1e-4 * y[:2, 4:].abs().max().item()
+    # (6) first 4 clips against the CPU oracle (SURVEY 8d cfg2 parity subset)
+    from oracle import seld_oracle as so
+    ref = so.logmel_iv(x[:4].cpu().numpy(), ext.stft_extractor.window.cpu().numpy(),
+                       ext.mel_scale.fb.cpu().numpy(), 1024, 240, np.float64)
+    assert_blocks_close(y[:4].cpu().numpy(), ref, 4, what='cfg2 clips 0-3')
