@@ -18,6 +18,8 @@ struct seld_plan {
     int sm_count;
     int n_fft;
     size_t smem_optin;
+    int iv_kernel;         // 3 / 2: generation of the 4-channel IV kernel in use; 0: general kernel only
+    bool use_iv2;          // segment-form bank + shared memory fit: 4-channel IV goes to the iv2 kernel
     void* blob;            // one device allocation holding every table
 };
 
@@ -51,6 +53,52 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     if (wt.empty()) wt.assign(4, 0.0f);
     const int n_mels_pad = (n_mels + 3) & ~3;
 
+
+    // ---- segment form for the iv2 kernel: bin k feeds only bands s_k-1 and s_k (true for every
+    // triangular bank whose bands overlap their neighbours only); runs = maximal stretches of one
+    // segment inside one lane's 16-bin chunk (bin 512 rides with lane 31).
+    std::vector<float> wab(32 * 36, 0.0f);
+    std::vector<uint32_t> runmask(32, 0);
+    std::vector<int> g0(32, 0), gseg(n_mels + 2, 0);
+    int fast_ok = (F == 513);
+    {
+        std::vector<int> seg(F, 0);
+        int sprev = 0;
+        for (int k = 0; k < F && fast_ok; ++k) {
+            int first = -1, last = -1, cnt = 0;
+            for (int m = 0; m < n_mels; ++m)
+                if (fb_host[(size_t)k * n_mels + m] != 0.0f) { if (first < 0) first = m; last = m; ++cnt; }
+            int sk;
+            if (cnt == 0) sk = sprev;
+            else if (cnt == 1) sk = (sprev == first || sprev == first + 1) ? sprev : first;
+            else if (cnt == 2 && last == first + 1) sk = last;
+            else { fast_ok = 0; break; }
+            if (sk < sprev) { fast_ok = 0; break; }
+            seg[k] = sk; sprev = sk;
+        }
+        if (fast_ok) {
+            int g = -1;
+            std::vector<int> run_seg;
+            for (int k = 0; k < F; ++k) {
+                const int c = k < 512 ? k / 16 : 31, j = k - 16 * c;
+                const bool start = (k == 0) || seg[k] != seg[k - 1] || (j == 0);
+                if (start) { ++g; run_seg.push_back(seg[k]); if (j > 0) runmask[c] |= (1u << j); }
+                if (j == 0) g0[c] = g;
+                const int sk = seg[k];
+                wab[c * 36 + 2 * j] = sk >= 1 ? fb_host[(size_t)k * n_mels + sk - 1] : 0.0f;
+                wab[c * 36 + 2 * j + 1] = sk < n_mels ? fb_host[(size_t)k * n_mels + sk] : 0.0f;
+            }
+            const int nruns = g + 1;
+            if (2 * nruns > 512) fast_ok = 0;        // partial sums live in the first words of a row
+            for (int sgm = 0; sgm <= n_mels + 1; ++sgm) {
+                int n = 0;
+                for (int r = 0; r < nruns; ++r) if (run_seg[r] < sgm) ++n;
+                gseg[sgm] = n;
+            }
+        }
+    }
+    const int gseg_pad = (n_mels + 2 + 3) & ~3;
+
     // ---- twiddles W1024^(ka*j), window * 0.5
     std::vector<float> tw(2 * 1024), win(n_fft);
     for (int ka = 0; ka < 32; ++ka)
@@ -60,6 +108,16 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
             tw[2 * (ka * 32 + j) + 1] = (float)(-sin(ang));
         }
     for (int i = 0; i < n_fft; ++i) win[i] = 0.5f * window_host[i];
+    std::vector<float> tw4(16 * 32 * 4), win2(16 * 32 * 2);
+    for (int q = 0; q < 16; ++q)
+        for (int l = 0; l < 32; ++l) {
+            const double a0 = 2.0 * M_PI * (double)((q * l) % 1024) / 1024.0;
+            const double a1 = 2.0 * M_PI * (double)(((q + 16) * l) % 1024) / 1024.0;
+            float* t = &tw4[(q * 32 + l) * 4];
+            t[0] = (float)cos(a0); t[1] = (float)cos(a1); t[2] = (float)sin(a0); t[3] = (float)sin(a1);
+            win2[(q * 32 + l) * 2] = win[32 * (2 * q) + l];
+            win2[(q * 32 + l) * 2 + 1] = win[32 * (2 * q + 1) + l];
+        }
 
     seld_plan* p = new (std::nothrow) seld_plan();
     if (!p) return SELD_ENOMEM;
@@ -76,7 +134,9 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     p->smem_optin = (size_t)smem_optin;
 
     const size_t b_tw = tw.size() * 4, b_win = win.size() * 4, b_wt = wt.size() * 4, b_i = (size_t)n_mels_pad * 4;
-    const size_t total = b_tw + b_win + b_wt + 3 * b_i;
+    const size_t b_wab = wab.size() * 4, b_rm = 32 * 4, b_g0 = 32 * 4, b_gs = (size_t)gseg_pad * 4;
+    const size_t b_tw4 = tw4.size() * 4, b_win2 = win2.size() * 4;
+    const size_t total = b_tw + b_win + b_wt + 3 * b_i + b_wab + b_rm + b_g0 + b_gs + b_tw4 + b_win2;
     e = cudaMalloc(&p->blob, total);
     if (e != cudaSuccess) { cudaSetDevice(prev); delete p; return cuda_fail(e); }
     std::vector<unsigned char> host(total, 0);
@@ -87,6 +147,12 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     memcpy(&host[o], blo.data(), n_mels * 4); const size_t o_lo = o; o += b_i;
     memcpy(&host[o], bcnt.data(), n_mels * 4); const size_t o_cnt = o; o += b_i;
     memcpy(&host[o], boff.data(), n_mels * 4); const size_t o_off = o; o += b_i;
+    memcpy(&host[o], wab.data(), b_wab); const size_t o_wab = o; o += b_wab;
+    memcpy(&host[o], runmask.data(), b_rm); const size_t o_rm = o; o += b_rm;
+    memcpy(&host[o], g0.data(), b_g0); const size_t o_g0 = o; o += b_g0;
+    memcpy(&host[o], gseg.data(), gseg.size() * 4); const size_t o_gs = o; o += b_gs;
+    memcpy(&host[o], tw4.data(), b_tw4); const size_t o_tw4 = o; o += b_tw4;
+    memcpy(&host[o], win2.data(), b_win2); const size_t o_win2 = o; o += b_win2;
     e = cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { cudaFree(p->blob); delete p; return cuda_fail(e); }
@@ -94,10 +160,18 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     unsigned char* d = (unsigned char*)p->blob;
     p->dev.tw = (const float2*)(d + o_tw);
     p->dev.win = (const float*)(d + o_win);
+    p->dev.tw4 = (const float4*)(d + o_tw4);
+    p->dev.win2 = (const float2*)(d + o_win2);
     p->dev.wt = (const float*)(d + o_wt);
     p->dev.blo = (const int*)(d + o_lo);
     p->dev.bcnt = (const int*)(d + o_cnt);
     p->dev.boff = (const int*)(d + o_off);
+    p->dev.wab = (const float*)(d + o_wab);
+    p->dev.runmask = (const uint32_t*)(d + o_rm);
+    p->dev.g0 = (const int*)(d + o_g0);
+    p->dev.gseg = (const int*)(d + o_gs);
+    p->dev.gseg_pad = gseg_pad;
+    p->dev.fast_ok = fast_ok;
     p->dev.nnz_pad = (int)wt.size();
     p->dev.n_mels = n_mels; p->dev.n_mels_pad = n_mels_pad;
     p->dev.hop = hop; p->dev.amin = amin; p->dev.eps = eps;
@@ -105,6 +179,14 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     // the tile (frames_per_tile-1)*hop + n_fft samples x 4 channels must fit next to the tables
     const int span = (((seld::foa_frames_per_tile() - 1) * hop + n_fft) + 3) & ~3;
     if (seld::foa_smem_bytes(p->dev, span) > p->smem_optin) { seld_plan_destroy(p); return SELD_EUNSUPPORTED; }
+    p->use_iv2 = false; p->iv_kernel = 0;
+    {
+        const char* force = getenv("SELD_IV_KERNEL");      // experiments: 1 (general), 2, 3
+        const int want = force ? atoi(force) : 2;          // measured: iv2 (8 warps) 0.46 ms vs iv3 (16 warps) 0.52 ms at cfg2
+        if (want >= 3 && seld::foa_iv3_supported(p->dev, p->smem_optin)) p->iv_kernel = 3;
+        else if (want >= 2 && seld::foa_iv2_supported(p->dev, p->smem_optin)) p->iv_kernel = 2;
+        p->use_iv2 = p->iv_kernel != 0;
+    }
     *out = p;
     return SELD_OK;
 }
@@ -122,21 +204,39 @@ extern "C" int64_t seld_num_frames(const seld_plan* p, int64_t L) {
 
 static int run_foa(const seld_plan* p, bool iv, const float* x, int64_t B, int C, int64_t L,
                    int64_t stride_b, int64_t stride_c, float* out, void* stream) {
-    if (!p || !x || !out || B < 0 || C < 1 || L < 1) return SELD_EINVAL;
+    if (!p || B < 0 || C < 1 || L < 1) return SELD_EINVAL;
     if (iv && C < 4) return SELD_EINVAL;               // intensityvector indexes channels 0..3
     if (L <= p->n_fft / 2) return SELD_ESHORT;         // reflect padding needs pad < L (torch.stft)
-    if (B == 0) return SELD_OK;
+    if (B == 0) return SELD_OK;                        // empty batch: nothing to enqueue (pointers may be null)
+    if (!x || !out) return SELD_EINVAL;
     const int64_t T = 1 + L / p->dev.hop;
-    const int fpt = seld::foa_frames_per_tile();
-    const int64_t tiles_per_clip = (T + fpt - 1) / fpt;
-    if (B * tiles_per_clip > INT32_MAX || T > INT32_MAX) return SELD_EUNSUPPORTED;
+    if (T > INT32_MAX) return SELD_EUNSUPPORTED;
     seld::FoaArgs a;
     a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
-    a.B = (int)B; a.C = C; a.Cout = C + (iv ? 3 : 0); a.T = (int)T;
+    a.B = (int)B; a.C = C; a.Cout = C + (iv ? 3 : 0); a.T = (int)T; a.c_lo = 0;
+    a.span = 0; a.vec_ok = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool general_iv = iv;
+    if (iv && p->use_iv2) {
+        // channels 0-3: log-mel + IV by the packed dual-FFT kernel; any further channels below
+        const int fpt = p->iv_kernel == 3 ? seld::foa_iv3_frames_per_tile() : seld::foa_iv2_frames_per_tile();
+        const int64_t tpc = (T + fpt - 1) / fpt;
+        if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
+        a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc);
+        cudaError_t e = p->iv_kernel == 3 ? seld::foa_iv3_launch(a, p->dev, p->sm_count, st)
+                                          : seld::foa_iv2_launch(a, p->dev, p->sm_count, st);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (C == 4) return SELD_OK;
+        a.c_lo = 4; general_iv = false;
+    }
+    const int fpt = seld::foa_frames_per_tile();
+    const int64_t tiles_per_clip = (T + fpt - 1) / fpt;
+    if (B * tiles_per_clip > INT32_MAX) return SELD_EUNSUPPORTED;
     a.tiles_per_clip = (int)tiles_per_clip; a.n_tiles = (int)(B * tiles_per_clip);
     a.span = (((fpt - 1) * p->dev.hop + p->n_fft) + 3) & ~3;
     a.vec_ok = (((uintptr_t)x & 15) == 0) && (stride_b % 4 == 0) && (stride_c % 4 == 0) && (p->dev.hop % 4 == 0);
-    cudaError_t e = seld::foa_launch(iv, a, p->dev, p->sm_count, (cudaStream_t)stream);
+    cudaError_t e = seld::foa_launch(general_iv, a, p->dev, p->sm_count, st);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return SELD_OK;

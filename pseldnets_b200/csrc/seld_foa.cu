@@ -196,9 +196,9 @@ foa_features_kernel(const FoaArgs a, const PlanDev pd) {
     const int hop = pd.hop, span = a.span, M = pd.n_mels;
 
     // channel group handled by this block row
-    const int c_base = blockIdx.y * 4;
+    const int c_base = a.c_lo + blockIdx.y * 4;
     const int nc = min(4, a.C - c_base);
-    const bool do_iv = kIV && blockIdx.y == 0;
+    const bool do_iv = kIV && c_base == 0;
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_clip;
@@ -327,7 +327,7 @@ static cudaError_t launch_t(const FoaArgs& a, const PlanDev& pd, int sm_count, c
     const size_t smem = foa_smem_bytes(pd, a.span);
     cudaError_t e = cudaFuncSetAttribute(foa_features_kernel<kIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int groups = (a.C + 3) / 4;
+    const int groups = (a.C - a.c_lo + 3) / 4;
     int gx = (2 * sm_count) / groups;
     if (gx < 1) gx = 1;
     if (gx > a.n_tiles) gx = a.n_tiles;

@@ -1,0 +1,288 @@
+// FOA log-mel + intensity-vector kernel, second generation ("iv2"): the headline path.
+//
+//   LogmelIV_Extractor.forward (feature.py:39-56) + intensityvector (feature.py:93-117) for the
+//   4-channel case, one warp per frame, warps fully independent (no block barrier in the loop).
+//
+// What changed against the first kernel (seld_foa.cu, kept as the general fallback):
+//   * both packed complex FFTs of a frame ((ch0,ch1) and (ch2,ch3)) run TOGETHER in the two
+//     halves of float2 registers: every butterfly is one FADD2/FMUL2/FFMA2 (sm_100a packed
+//     fp32), and window / twiddle loads are shared -> about half the issue slots;
+//   * samples are read straight from global memory with coalesced 128-byte warp loads (the
+//     1024-hop overlap of neighbouring frames is served by L1/L2) -> no staging buffer, no
+//     __syncthreads, no exposed staging latency;
+//   * all seven per-bin quantities of the frame are produced in one pass and written to seven
+//     swizzled shared-memory rows; the mel projection walks them ONCE: lane c owns bins
+//     [16c, 16c+16), accumulates per mel "segment" (the bins between two consecutive band
+//     centres feed exactly bands s-1 and s) as one FFMA2 per bin and feature, and leaves per-run
+//     partial sums that a second, band-per-lane step combines (out[m] = V[m] + U[m+1]).
+//     Conflict-free 128-bit reads, balanced lanes, 2 weights per bin instead of a band table.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "fft32.cuh"
+#include "seld_plan.h"
+
+namespace seld {
+
+constexpr int kRowWords = 528;            // 33 chunks of 16 bins (bin 512 opens chunk 32)
+constexpr int kRows = 7;                  // P0 P1 P2 P3 n1 n2 n3
+constexpr int kRegion = kRows * kRowWords;   // floats per warp; the 32x33 float2 exchange buffer (2112) aliases it
+constexpr int kWabStride = 36;            // floats per lane in the (a, b) weight table: 17 float2 + pad, 36*l mod 32 = 4l
+
+__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int W>
+__global__ void __launch_bounds__(W * 32, 1) 
+foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);                    // 1024 float2
+    float* win_s = reinterpret_cast<float*>(tw_s + 1024);                  // 1024
+    float* wab_s = win_s + 1024;                                           // 32 * kWabStride
+    int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
+    float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 1024; i += W * 32) { tw_s[i] = pd.tw[i]; win_s[i] = pd.win[i]; }
+    for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
+    for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
+    __syncthreads();
+
+    float* R = R_all + warp * kRegion;
+    float2* scratch = reinterpret_cast<float2*>(R);
+    const uint32_t runmask = pd.runmask[lane];
+    const int g0 = pd.g0[lane];
+    const int hop = pd.hop, M = pd.n_mels;
+    const float eps = pd.eps, amin = pd.amin;
+    // writer: bin k = lane + 32*kb lands at word 32*kb + wofs[kb & 3] of its row
+    int wofs[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) wofs[x] = 16 * (lane >> 4) + 4 * (((lane >> 2) & 3) ^ x) + (lane & 3);
+    // reader: lane owns chunk c = lane; logical quad i sits at word 16c + 4*(i ^ ((c >> 1) & 3))
+    int rofs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rofs[i] = 16 * lane + 4 * (i ^ ((lane >> 1) & 3));
+
+    const int64_t ch_stride = (int64_t)a.T * M;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_clip;
+        const int t = (tile - b * a.tiles_per_clip) * W + warp;
+        if (t >= a.T) continue;
+        const float* xb = a.x + (int64_t)b * a.stride_b;
+        const int64_t s0 = (int64_t)t * hop - 512;
+
+        float2 re[32], im[32];
+        // ---------------- load + window: re = (ch0, ch2), im = (ch1, ch3)
+        if (s0 >= 0 && s0 + 1024 <= a.L) {
+            const float* p0 = xb + s0 + lane;
+            const float* p1 = p0 + a.stride_c;
+            const float* p2 = p1 + a.stride_c;
+            const float* p3 = p2 + a.stride_c;
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                re[m] = make_float2(__ldg(p0 + 32 * m), __ldg(p2 + 32 * m));
+                im[m] = make_float2(__ldg(p1 + 32 * m), __ldg(p3 + 32 * m));
+            });
+        } else {                                                            // reflect padding at the clip edges
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                int64_t s = s0 + 32 * m + lane;
+                if (s < 0) s = -s;
+                if (s >= a.L) s = 2 * (a.L - 1) - s;
+                const float* p = xb + s;
+                re[m] = make_float2(__ldg(p), __ldg(p + 2 * a.stride_c));
+                im[m] = make_float2(__ldg(p + a.stride_c), __ldg(p + 3 * a.stride_c));
+            });
+        }
+        static_for<0, 32>([&](auto mi) {
+            constexpr int m = decltype(mi)::value;
+            const float w = win_s[32 * m + lane];
+            re[m] = vmuls(re[m], w);
+            im[m] = vmuls(im[m], w);
+        });
+
+        // ---------------- two 1024-point FFTs at once: 32-pt, twiddle, exchange, 32-pt
+        fft32(re, im);
+        static_for<1, 32>([&](auto pi) {
+            constexpr int p = decltype(pi)::value;
+            constexpr int ka = brev5(p);
+            const float2 w = tw_s[ka * 32 + lane];                          // (cos, -sin)
+            const float2 r = re[p], i = im[p];
+            re[p] = vfmas(i, -w.y, vmuls(r, w.x));
+            im[p] = vfmas(i, w.x, vmuls(r, w.y));
+        });
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = re[p]; });
+        __syncwarp();
+        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; re[j] = scratch[lane * 33 + j]; });
+        __syncwarp();
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = im[p]; });
+        __syncwarp();
+        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; im[j] = scratch[lane * 33 + j]; });
+        __syncwarp();
+        fft32(re, im);                                                      // position p: Z[lane + 32*brev5(p)]
+
+        // ---------------- per-bin quantities -> 7 rows
+        {
+            const int src = (32 - lane) & 31;
+            static_for<0, 17>([&](auto kbi) {
+                constexpr int kb = decltype(kbi)::value;
+                constexpr int p = brev5(kb & 31);
+                const float2 zr = re[p], zi = im[p];
+                float2 pr, pi;
+                if constexpr (kb == 16) {
+                    pr = zr; pi = zi;
+                } else {
+                    constexpr int pp = brev5(31 - kb), p0 = brev5((32 - kb) & 31);
+                    pr.x = __shfl_sync(0xffffffffu, re[pp].x, src);
+                    pr.y = __shfl_sync(0xffffffffu, re[pp].y, src);
+                    pi.x = __shfl_sync(0xffffffffu, im[pp].x, src);
+                    pi.y = __shfl_sync(0xffffffffu, im[pp].y, src);
+                    if (lane == 0) { pr = re[p0]; pi = im[p0]; }
+                }
+                // window was pre-scaled by 0.5: A = Z[k] + conj(Z[N-k]), B = (Z[k] - conj(Z[N-k])) / i
+                const float2 ar = vadd(zr, pr), ai = vsub(zi, pi);          // (X0, X2)
+                const float2 br = vadd(zi, pi), bi = vsub(pr, zr);          // (X1, X3)
+                const float2 p02 = __ffma2_rn(ai, ai, __fmul2_rn(ar, ar));
+                const float2 p13 = __ffma2_rn(bi, bi, __fmul2_rn(br, br));
+                const float2 i13 = vfmas(bi, ai.x, vmuls(br, ar.x));        // Re(conj(X0) X1), Re(conj(X0) X3)
+                const float i2 = fmaf(ai.x, ai.y, ar.x * ar.y);             // Re(conj(X0) X2)
+                const float s = fmaf(i13.y, i13.y, fmaf(i2, i2, i13.x * i13.x));
+                const float nrm = (s > 1e-37f ? s * rsqrt_ftz(s) : 0.0f) + eps;
+                const float inv = rcp_ftz(nrm);
+                if (kb < 16 || lane == 0) {
+                    float* q = R + 32 * kb + wofs[kb & 3];
+                    q[0 * kRowWords] = p02.x;
+                    q[1 * kRowWords] = p13.x;
+                    q[2 * kRowWords] = p02.y;
+                    q[3 * kRowWords] = p13.y;
+                    q[4 * kRowWords] = i13.x * inv;
+                    q[5 * kRowWords] = i2 * inv;
+                    q[6 * kRowWords] = i13.y * inv;
+                }
+            });
+        }
+        __syncwarp();
+
+        // ---------------- mel step 1: chunk walk, per-run partial sums (U, V) left in the rows
+        {
+            float2 wv[17];
+            const float4* wp = reinterpret_cast<const float4*>(wab_s + lane * kWabStride);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = wp[i];
+                wv[2 * i] = make_float2(v.x, v.y);
+                wv[2 * i + 1] = make_float2(v.z, v.w);
+            }
+            wv[16] = *reinterpret_cast<const float2*>(wab_s + lane * kWabStride + 32);
+
+            auto walk = [&](auto f0c, auto nfc) {
+                constexpr int f0 = decltype(f0c)::value, nf = decltype(nfc)::value;
+                float q[nf][17];
+#pragma unroll
+                for (int f = 0; f < nf; ++f) {
+                    const float* row = R + (f0 + f) * kRowWords;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 v = *reinterpret_cast<const float4*>(row + rofs[i]);
+                        q[f][4 * i] = v.x; q[f][4 * i + 1] = v.y; q[f][4 * i + 2] = v.z; q[f][4 * i + 3] = v.w;
+                    }
+                    q[f][16] = lane == 31 ? row[512] : 0.0f;
+                }
+                __syncwarp();                                               // everyone holds its bins: rows may be overwritten
+                float2 acc[nf];
+                float2* po = reinterpret_cast<float2*>(R + f0 * kRowWords) + g0;
+#pragma unroll
+                for (int f = 0; f < nf; ++f) acc[f] = vmuls(wv[0], q[f][0]);
+                static_for<1, 17>([&](auto ji) {
+                    constexpr int j = decltype(ji)::value;
+                    if ((runmask >> j) & 1u) {                              // a new run starts at this bin
+#pragma unroll
+                        for (int f = 0; f < nf; ++f) {
+                            po[f * (kRowWords / 2)] = acc[f];
+                            acc[f] = vmuls(wv[j], q[f][j]);
+                        }
+                        ++po;
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < nf; ++f) acc[f] = vfmas(wv[j], q[f][j], acc[f]);
+                    }
+                });
+#pragma unroll
+                for (int f = 0; f < nf; ++f) po[f * (kRowWords / 2)] = acc[f];
+            };
+            walk(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
+            walk(std::integral_constant<int, 4>{}, std::integral_constant<int, 3>{});
+        }
+        __syncwarp();
+
+        // ---------------- mel step 2: band per lane, out[m] = sum V(runs of segment m) + sum U(runs of segment m+1)
+        {
+            float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
+            const float2* P = reinterpret_cast<const float2*>(R);
+            for (int m = lane; m < M; m += 32) {
+                const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
+                float v[kRows];
+#pragma unroll
+                for (int f = 0; f < kRows; ++f) v[f] = 0.0f;
+                for (int g = ga; g < gb; ++g) {
+#pragma unroll
+                    for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].y;
+                }
+                for (int g = gb; g < gc; ++g) {
+#pragma unroll
+                    for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].x;
+                }
+#pragma unroll
+                for (int f = 0; f < 4; ++f)                                  // 10*log10(max(v, amin))
+                    ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
+#pragma unroll
+                for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
+            }
+        }
+        __syncwarp();                                                       // rows are reused by the next frame's exchange
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int W>
+static size_t iv2_smem_bytes(const PlanDev& pd) {
+    return (size_t)(2 * 1024 + 1024 + 32 * kWabStride + pd.gseg_pad + W * kRegion) * sizeof(float);
+}
+
+// Warps (= frames) per block.  One block per SM; more warps hide latency, fewer leave more
+// registers per thread (8 -> 255, 12 -> 168; warps are allocated in fours).  SELD_IV2_WARPS overrides for experiments.
+static int iv2_warps() {
+    static int w = [] {
+        const char* e = getenv("SELD_IV2_WARPS");
+        const int v = e ? atoi(e) : 8;                       // measured at cfg2: 8 -> 0.46 ms, 12 (spills) -> 0.51 ms
+        return (v == 8 || v == 12) ? v : 8;
+    }();
+    return w;
+}
+
+bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin) {
+    return pd.fast_ok && iv2_smem_bytes<12>(pd) <= smem_optin;
+}
+
+int foa_iv2_frames_per_tile() { return iv2_warps(); }
+
+template <int W>
+static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
+    const size_t smem = iv2_smem_bytes<W>(pd);
+    cudaError_t e = cudaFuncSetAttribute(foa_iv2_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
+    foa_iv2_kernel<W><<<gx, W * 32, smem, st>>>(a, pd);
+    return cudaGetLastError();
+}
+
+cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
+    switch (iv2_warps()) {
+        case 12: return iv2_launch_t<12>(a, pd, sm_count, st);
+        default: return iv2_launch_t<8>(a, pd, sm_count, st);
+    }
+}
+
+}  // namespace seld

@@ -10,10 +10,20 @@ namespace seld {
 struct PlanDev {
     const float2* tw;     // [32][32] (cos, -sin)(2*pi*ka*j/1024) at [ka*32 + j]
     const float* win;     // [n_fft] analysis window * 0.5
+    const float4* tw4;    // iv3: [16][32] (cos q, cos q+16, sin q, sin q+16)(2*pi*ka*lane/1024)
+    const float2* win2;   // iv3: [16][32] 0.5 * (w[32*2p + lane], w[32*(2p+1) + lane])
     const float* wt;      // band-sparse mel weights, band after band
     const int* blo;       // [n_mels] first bin of the band's support
     const int* bcnt;      // [n_mels] bins in the support
     const int* boff;      // [n_mels] offset of the band's weights in wt
+    // segment form of the bank for the iv2 kernel (valid when fast_ok): every bin k feeds only
+    // bands s_k-1 and s_k with weights (a_k, b_k); lane c owns bins [16c, 16c+16) (+512 for c=31)
+    const float* wab;     // [32][36] (a, b) pairs per lane, 17 used
+    const uint32_t* runmask;  // [32] bit j: a new run (segment change) starts at the lane's bin j
+    const int* g0;        // [32] index of the lane's first run
+    const int* gseg;      // [n_mels + 2] first run of segment s; runs of s are [gseg[s], gseg[s+1])
+    int gseg_pad;         // ints reserved for gseg in shared memory (multiple of 4)
+    int fast_ok;          // bank has the segment structure and the run table fits
     int nnz_pad;          // floats in wt (multiple of 4)
     int n_mels, n_mels_pad;
     int hop;
@@ -25,7 +35,8 @@ struct FoaArgs {
     int64_t stride_b, stride_c;
     float* out;              // (B, Cout, T, M) contiguous
     int64_t L;
-    int B, C, Cout, T;
+    int B, C, Cout, T;       // C = channels of x, Cout = channels of out
+    int c_lo;                // first input channel this launch covers (log-mel of channels c_lo..C-1)
     int tiles_per_clip, n_tiles;
     int span;                // staged samples per channel per tile (multiple of 4)
     int vec_ok;              // x base/strides allow 16-byte loads
@@ -34,5 +45,15 @@ struct FoaArgs {
 size_t foa_smem_bytes(const PlanDev& pd, int span);
 int foa_frames_per_tile();
 cudaError_t foa_launch(bool iv, const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
+
+// second-generation 4-channel log-mel + IV kernel (seld_foa_iv2.cu)
+bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin);
+int foa_iv2_frames_per_tile();
+cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
+
+// third-generation kernel: two warps per frame (seld_foa_iv3.cu)
+bool foa_iv3_supported(const PlanDev& pd, size_t smem_optin);
+int foa_iv3_frames_per_tile();
+cudaError_t foa_iv3_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
 
 }  // namespace seld

@@ -177,8 +177,10 @@ def test_full_size_properties_cfg2():
     xf = x[:4].clone()
     xf[:, 2] = -xf[:, 2]
     yf = ext(xf)
-    assert torch.equal(yf[:, :4], y[:4, :4])
-    assert torch.allclose(yf[:, 5], -y[:4, 5], atol=1e-7) and torch.allclose(yf[:, 4], y[:4, 4], atol=1e-7)
+    tol_lm = 1e-4 * y[:4, :4].abs().max().item()
+    tol_iv = 1e-4 * y[:4, 4:].abs().max().item()
+    assert (yf[:, :4] - y[:4, :4]).abs().max().item() < tol_lm
+    assert (yf[:, 5] + y[:4, 5]).abs().max().item() < tol_iv and (yf[:, 4] - y[:4, 4]).abs().max().item() < tol_iv
     # (4) swapping channels 1 and 3 swaps their log-mel and IV maps
     xs = x[:4][:, [0, 3, 2, 1]].contiguous()
     ys = ext(xs)
