@@ -53,6 +53,20 @@ int seld_logmel_iv_f32(const seld_plan* plan, const float* x, int64_t B, int C, 
 int seld_logmel_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
                     int64_t stride_b, int64_t stride_c, float* out, void* stream);
 
+/* MIC features: Features_Extractor_MIC._spectrogram / _get_logmel_spectrogram / _get_gcc
+ * (feature.py:146-175) assembled as preprocess.py:546-556.  x (B, C=4, L) -> out
+ * (B, 4 + 6, T, n_mels), T = L / hop: 4 log-mel planes (librosa.power_to_db: amin clamp, then a
+ * floor at the plane's maximum - top_db; pass top_db < 0 for "None") followed by the 6
+ * GCC-PHAT planes of mic pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3), lags [-n_mels/2, n_mels/2).
+ * Frames use librosa.stft's zero ('constant') centre padding.  The plan's fb is the mel bank
+ * (librosa.filters.mel(sr, n_fft, n_mels).T).  `workspace` is device scratch of at least
+ * seld_workspace_bytes(plan, B, C) bytes (per-plane running maxima). */
+int64_t seld_num_frames_mic(const seld_plan* plan, int64_t L);
+size_t seld_workspace_bytes(const seld_plan* plan, int64_t B, int C);
+int seld_logmel_gcc_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
+                        int64_t stride_b, int64_t stride_c, float top_db, float* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Kernels enqueued by this library since load (all entry points, all plans). */
 uint64_t seld_launch_count(void);
 /* cudaError_t of the most recent failing runtime call on this thread (0 if none). */

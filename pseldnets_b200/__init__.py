@@ -1,7 +1,8 @@
 """B200-native SELD feature front-end: a drop-in for the extractors of Jinbo-Hu/PSELDNets
 (`src/utils/feature.py`), computed by fused sm_100a CUDA kernels behind a C ABI."""
 from .config import get_afextractor
-from .feature import LogmelIV_Extractor, Logmel_Extractor
+from .feature import Features_Extractor_MIC, LogmelGCC_Extractor, LogmelIV_Extractor, Logmel_Extractor
 
-__all__ = ['LogmelIV_Extractor', 'Logmel_Extractor', 'get_afextractor']
+__all__ = ['LogmelIV_Extractor', 'Logmel_Extractor', 'LogmelGCC_Extractor', 'Features_Extractor_MIC',
+           'get_afextractor']
 __version__ = '0.1'

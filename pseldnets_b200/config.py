@@ -8,6 +8,10 @@ def get_afextractor(cfg):
         afextractor = feature.LogmelIV_Extractor(cfg)
     elif cfg['data']['audio_feature'] == 'logmel':
         afextractor = feature.Logmel_Extractor(cfg)
+    elif cfg['data']['audio_feature'] == 'logmelgcc':
+        # the reference returns None here (MIC features come from its offline numpy class);
+        # this build adds the on-GPU module for the same features
+        afextractor = feature.LogmelGCC_Extractor(cfg)
     else:
         afextractor = None
     return afextractor

@@ -252,6 +252,41 @@ extern "C" int seld_logmel_f32(const seld_plan* p, const float* x, int64_t B, in
     return run_foa(p, false, x, B, C, L, stride_b, stride_c, out, stream);
 }
 
+extern "C" int64_t seld_num_frames_mic(const seld_plan* p, int64_t L) {
+    if (!p || L < 0) return SELD_EINVAL;
+    return L / p->dev.hop;
+}
+
+extern "C" size_t seld_workspace_bytes(const seld_plan* p, int64_t B, int C) {
+    if (!p || B < 0 || C < 1) return 0;
+    return (size_t)B * (size_t)C * sizeof(int);
+}
+
+extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,
+                                   int64_t stride_b, int64_t stride_c, float top_db, float* out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p || B < 0 || C < 1 || L < 1) return SELD_EINVAL;
+    if (C != 4) return SELD_EUNSUPPORTED;              // the CUDA path covers the 4-mic arrays of DCASE2021 / STARSS23
+    if (!seld::mic_supported(p->dev, p->smem_optin)) return SELD_EUNSUPPORTED;
+    const int64_t T = L / p->dev.hop;
+    if (B == 0 || T == 0) return SELD_OK;
+    if (!x || !out || !workspace) return SELD_EINVAL;
+    if (workspace_bytes < seld_workspace_bytes(p, B, C)) return SELD_EINVAL;
+    if (T > INT32_MAX) return SELD_EUNSUPPORTED;
+    const int fpt = seld::mic_frames_per_tile();
+    const int64_t tpc = (T + fpt - 1) / fpt;
+    if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
+    seld::FoaArgs a;
+    a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
+    a.B = (int)B; a.C = C; a.Cout = C + C * (C - 1) / 2; a.T = (int)T; a.c_lo = 0;
+    a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.span = 0; a.vec_ok = 0;
+    const bool use_top_db = top_db >= 0.0f;
+    cudaError_t e = seld::mic_launch(a, p->dev, (int*)workspace, top_db, use_top_db, p->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(use_top_db ? 2 : 1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
 extern "C" uint64_t seld_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int seld_last_cuda_error(void) { return g_last_cuda; }
 

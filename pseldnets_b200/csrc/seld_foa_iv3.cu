@@ -21,85 +21,25 @@
 #include <stdlib.h>
 
 #include "fft32.cuh"
+#include "mel_seg.cuh"
 #include "seld_plan.h"
 
 namespace seld {
 
 namespace iv3 {
-constexpr int kRowWords = 528;            // 33 chunks of 16 bins (bin 512 opens chunk 32)
+using melseg::kRowWords;
+using melseg::kWabStride;
+using melseg::mel_walk;
+using melseg::mel_combine;
 constexpr int kPlane = 32 * 34;           // exchange plane: [ka][lane], row stride 34 (even: 64-bit reads)
 constexpr int kArea = 2 * kPlane;         // re + im plane of one warp
 constexpr int kRegion = 2 * kArea;        // floats per frame (warp pair); the 7 rows (3696) alias it
-constexpr int kWabStride = 36;
 
-__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+using melseg::rsqrt_ftz;
+using melseg::rcp_ftz;
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Walk NF rows (compile-time row ids) of the frame region: per-run (U, V) partial sums are left in
-// the first words of each row.  wv: the lane's 17 (a, b) weight pairs.
-template <int NF, int R0, int R1, int R2>
-__device__ __forceinline__ void mel_walk(float* R, const float2 (&wv)[17], const int (&rofs)[4],
-                                         uint32_t runmask, int g0, int lane) {
-    constexpr int rows[3] = {R0, R1, R2};
-    float q[NF][17];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        const float* row = R + rows[f] * kRowWords;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(row + rofs[i]);
-            q[f][4 * i] = v.x; q[f][4 * i + 1] = v.y; q[f][4 * i + 2] = v.z; q[f][4 * i + 3] = v.w;
-        }
-        q[f][16] = lane == 31 ? row[512] : 0.0f;
-    }
-    __syncwarp();                                                   // every lane holds its bins: rows may be overwritten
-    float2 acc[NF];
-    int po = g0;                                                    // float2 index of the lane's current run
-#pragma unroll
-    for (int f = 0; f < NF; ++f) acc[f] = vmuls(wv[0], q[f][0]);
-    static_for<1, 17>([&](auto ji) {
-        constexpr int j = decltype(ji)::value;
-        if ((runmask >> j) & 1u) {                                  // a new run starts at this bin
-#pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                reinterpret_cast<float2*>(R + rows[f] * kRowWords)[po] = acc[f];
-                acc[f] = vmuls(wv[j], q[f][j]);
-            }
-            ++po;
-        } else {
-#pragma unroll
-            for (int f = 0; f < NF; ++f) acc[f] = vfmas(wv[j], q[f][j], acc[f]);
-        }
-    });
-#pragma unroll
-    for (int f = 0; f < NF; ++f) reinterpret_cast<float2*>(R + rows[f] * kRowWords)[po] = acc[f];
-}
-
-// Band-per-lane combine of NF rows: out[m] = sum V(runs of segment m) + sum U(runs of segment m+1).
-template <int NF, int R0, int R1, int R2, int R3, bool kDb>
-__device__ __forceinline__ void mel_combine(const float* R, const int* gseg_s, int M, int lane, float amin,
-                                            float* const (&o)[4]) {
-    constexpr int rows[4] = {R0, R1, R2, R3};
-    for (int m = lane; m < M; m += 32) {
-        const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
-        float v[NF];
-#pragma unroll
-        for (int f = 0; f < NF; ++f) v[f] = 0.0f;
-        for (int g = ga; g < gb; ++g) {
-#pragma unroll
-            for (int f = 0; f < NF; ++f) v[f] += reinterpret_cast<const float2*>(R + rows[f] * kRowWords)[g].y;
-        }
-        for (int g = gb; g < gc; ++g) {
-#pragma unroll
-            for (int f = 0; f < NF; ++f) v[f] += reinterpret_cast<const float2*>(R + rows[f] * kRowWords)[g].x;
-        }
-#pragma unroll
-        for (int f = 0; f < NF; ++f)
-            o[f][m] = kDb ? 3.01029995663981195f * __log2f(fmaxf(v[f], amin)) : v[f];   // 10*log10(max(v, amin))
-    }
-}
 }  // namespace iv3
 
 template <int NP>

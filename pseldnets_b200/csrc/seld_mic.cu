@@ -1,0 +1,326 @@
+// MIC feature kernel: log-mel (top_db-limited) + GCC-PHAT for a 4-microphone array.
+//
+// Reference behaviour restated (not ported): /root/reference/src/utils/feature.py
+//   Features_Extractor_MIC._spectrogram :146-153 (librosa.stft: zero 'constant' centre padding,
+//   frames cropped to int(L/hop)), _get_logmel_spectrogram :155-162 (|X|^2 @ mel_bank,
+//   power_to_db with top_db=80 per channel plane), _get_gcc :164-175 (R = conj(X_m) X_n,
+//   irfft(exp(j*angle(R))), lags [-M/2, M/2)), assembled channel-first as preprocess.py:549-556.
+//
+// One warp per frame, warps independent.  Per frame:
+//   1. both packed complex FFTs ((mic0,mic1), (mic2,mic3)) together in float2 halves (as iv2);
+//   2. untangle -> the four spectra go to shared memory (4 x 513 complex), powers to 4 swizzled rows;
+//   3. segment-walk mel of the 4 power rows -> dB, stored unclamped; the running per-(clip, mic)
+//      maximum is kept in registers and flushed with one atomicMax per clip change;
+//   4. GCC-PHAT: two passes of two packed inverse transforms.  A transform's input is
+//      Z = ph_a + i*ph_b for two mic pairs (its real/imag outputs are the two correlations); lane l
+//      builds Z[l + 32m] for all m from the shared spectra (bins above 512 are the conjugates of
+//      1024-k), runs the 32-point inverse stage in registers, twiddles, exchanges, and -- because
+//      only lags [-32, 32) are kept -- evaluates just the two needed outputs of the second stage.
+// A second, element-wise kernel applies the top_db floor once every frame's maximum is known.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft32.cuh"
+#include "mel_seg.cuh"
+#include "seld_plan.h"
+
+namespace seld {
+namespace mic {
+using namespace melseg;
+
+constexpr int kW = 8;                      // warps (frames) per block
+constexpr int kSpecStride = 516;           // float2 per channel spectrum (513 + pad)
+constexpr int kSpec = 4 * kSpecStride * 2; // floats: four spectra
+constexpr int kRowsArea = 4 * kRowWords;   // floats: 4 power rows == 32x33 float2 exchange buffer
+constexpr int kRegion = kSpec + kRowsArea;
+
+// order-preserving float <-> int key for atomicMax
+__device__ __forceinline__ int f2key(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+
+// unit phasor of conj(a) * b; 1 when the product vanishes (np.angle(0) = 0)
+__device__ __forceinline__ float2 phat(float2 a, float2 b) {
+    const float re = fmaf(a.y, b.y, a.x * b.x), im = fmaf(-a.y, b.x, a.x * b.y);
+    const float s = fmaf(im, im, re * re);
+    if (!(s > 1e-37f)) {
+        // rescale tiny products before normalising (keeps the phase of quiet bins)
+        const float m = fmaxf(fabsf(re), fabsf(im));
+        if (m == 0.0f) return make_float2(1.0f, 0.0f);
+        const float r2 = re / m, i2 = im / m;
+        const float inv = rsqrtf(fmaf(i2, i2, r2 * r2));
+        return make_float2(r2 * inv, i2 * inv);
+    }
+    const float inv = rsqrt_ftz(s);
+    return make_float2(re * inv, im * inv);
+}
+}  // namespace mic
+
+__global__ void __launch_bounds__(mic::kW * 32, 1)
+mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey) {
+    using namespace mic;
+    constexpr int W = kW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);                    // 1024 float2 (cos, -sin)
+    float* win_s = reinterpret_cast<float*>(tw_s + 1024);                  // 1024
+    float* wab_s = win_s + 1024;                                           // 32 * kWabStride
+    int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
+    float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 1024; i += W * 32) { tw_s[i] = pd.tw[i]; win_s[i] = pd.win[i]; }
+    for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
+    for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
+    __syncthreads();
+
+    float2* spec = reinterpret_cast<float2*>(R_all + warp * kRegion);      // [4][kSpecStride]
+    float* R = R_all + warp * kRegion + kSpec;                             // 4 rows / exchange buffer
+    float2* scratch = reinterpret_cast<float2*>(R);
+    const uint32_t runmask = pd.runmask[lane];
+    const int g0 = pd.g0[lane];
+    const int hop = pd.hop, M = pd.n_mels;
+    const float amin = pd.amin;
+    int wofs[4], rofs[4];
+    lane_offsets(lane, wofs, rofs);
+    const int64_t ch_stride = (int64_t)a.T * M;
+    const int src = (32 - lane) & 31;
+
+    int cur_b = -1;
+    float rmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    auto flush_max = [&]() {
+        if (cur_b < 0) return;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = rmax[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0) atomicMax(maxkey + cur_b * 4 + c, f2key(v));
+            rmax[c] = -INFINITY;
+        }
+    };
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_clip;
+        const int t = (tile - b * a.tiles_per_clip) * W + warp;
+        if (t >= a.T) continue;
+        if (b != cur_b) { flush_max(); cur_b = b; }
+        const float* xb = a.x + (int64_t)b * a.stride_b;
+        const int64_t s0 = (int64_t)t * hop - 512;
+
+        float2 re[32], im[32];
+        // ---------------- load + window: re = (mic0, mic2), im = (mic1, mic3); zeros outside the clip
+        if (s0 >= 0 && s0 + 1024 <= a.L) {
+            const float* p0 = xb + s0 + lane;
+            const float* p1 = p0 + a.stride_c;
+            const float* p2 = p1 + a.stride_c;
+            const float* p3 = p2 + a.stride_c;
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                re[m] = make_float2(__ldg(p0 + 32 * m), __ldg(p2 + 32 * m));
+                im[m] = make_float2(__ldg(p1 + 32 * m), __ldg(p3 + 32 * m));
+            });
+        } else {
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                const int64_t s = s0 + 32 * m + lane;
+                const bool in = s >= 0 && s < a.L;
+                const float* p = xb + (in ? s : 0);
+                re[m] = in ? make_float2(__ldg(p), __ldg(p + 2 * a.stride_c)) : make_float2(0.f, 0.f);
+                im[m] = in ? make_float2(__ldg(p + a.stride_c), __ldg(p + 3 * a.stride_c)) : make_float2(0.f, 0.f);
+            });
+        }
+        static_for<0, 32>([&](auto mi) {
+            constexpr int m = decltype(mi)::value;
+            const float w = win_s[32 * m + lane];
+            re[m] = vmuls(re[m], w);
+            im[m] = vmuls(im[m], w);
+        });
+
+        // ---------------- forward: two 1024-point FFTs at once
+        fft32(re, im);
+        static_for<1, 32>([&](auto pi) {
+            constexpr int p = decltype(pi)::value;
+            constexpr int ka = brev5(p);
+            const float2 w = tw_s[ka * 32 + lane];
+            const float2 r = re[p], i = im[p];
+            re[p] = vfmas(i, -w.y, vmuls(r, w.x));
+            im[p] = vfmas(i, w.x, vmuls(r, w.y));
+        });
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = re[p]; });
+        __syncwarp();
+        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; re[j] = scratch[lane * 33 + j]; });
+        __syncwarp();
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = im[p]; });
+        __syncwarp();
+        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; im[j] = scratch[lane * 33 + j]; });
+        __syncwarp();
+        fft32(re, im);
+
+        // ---------------- untangle: spectra -> spec[c][k], powers -> rows
+        static_for<0, 17>([&](auto kbi) {
+            constexpr int kb = decltype(kbi)::value;
+            constexpr int p = brev5(kb & 31);
+            const float2 zr = re[p], zi = im[p];
+            float2 pr, pi;
+            if constexpr (kb == 16) {
+                pr = zr; pi = zi;
+            } else {
+                constexpr int pp = brev5(31 - kb), p0 = brev5((32 - kb) & 31);
+                pr.x = __shfl_sync(0xffffffffu, re[pp].x, src);
+                pr.y = __shfl_sync(0xffffffffu, re[pp].y, src);
+                pi.x = __shfl_sync(0xffffffffu, im[pp].x, src);
+                pi.y = __shfl_sync(0xffffffffu, im[pp].y, src);
+                if (lane == 0) { pr = re[p0]; pi = im[p0]; }
+            }
+            const float2 ar = vadd(zr, pr), ai = vsub(zi, pi);              // (X0, X2)
+            const float2 br = vadd(zi, pi), bi = vsub(pr, zr);              // (X1, X3)
+            const float2 p02 = __ffma2_rn(ai, ai, __fmul2_rn(ar, ar));
+            const float2 p13 = __ffma2_rn(bi, bi, __fmul2_rn(br, br));
+            if (kb < 16 || lane == 0) {
+                const int k = lane + 32 * kb;
+                spec[0 * kSpecStride + k] = make_float2(ar.x, ai.x);
+                spec[1 * kSpecStride + k] = make_float2(br.x, bi.x);
+                spec[2 * kSpecStride + k] = make_float2(ar.y, ai.y);
+                spec[3 * kSpecStride + k] = make_float2(br.y, bi.y);
+                float* q = R + 32 * kb + wofs[kb & 3];
+                q[0 * kRowWords] = p02.x;
+                q[1 * kRowWords] = p13.x;
+                q[2 * kRowWords] = p02.y;
+                q[3 * kRowWords] = p13.y;
+            }
+        });
+        __syncwarp();
+
+        // ---------------- log-mel of the four power rows (unclamped dB + running maximum)
+        float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
+        {
+            float2 wv[17];
+            load_weights(wab_s, lane, wv);
+            mel_walk<4, 0, 1, 2, 3>(R, wv, rofs, runmask, g0, lane);
+            __syncwarp();
+            for (int m = lane; m < M; m += 32) {
+                const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int g = ga; g < gb; ++g) {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) v[f] += reinterpret_cast<const float2*>(R + f * kRowWords)[g].y;
+                }
+                for (int g = gb; g < gc; ++g) {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) v[f] += reinterpret_cast<const float2*>(R + f * kRowWords)[g].x;
+                }
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const float db = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
+                    rmax[f] = fmaxf(rmax[f], db);
+                    ob[f * ch_stride + m] = db;
+                }
+            }
+            __syncwarp();                                                   // rows become the exchange buffer again
+        }
+
+        // ---------------- GCC-PHAT: pass 0 = pairs (01,02 | 03,12), pass 1 = pairs (13,23 | -, -)
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            // Z1 = ph(a1) + i ph(b1) in .x halves, Z2 = ph(a2) + i ph(b2) in .y halves
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                const int k = lane + 32 * m;
+                const bool up = k > 512;
+                const int kk = up ? 1024 - k : k;
+                float2 X0 = spec[0 * kSpecStride + kk], X1 = spec[1 * kSpecStride + kk];
+                float2 X2 = spec[2 * kSpecStride + kk], X3 = spec[3 * kSpecStride + kk];
+                if (up) { X0.y = -X0.y; X1.y = -X1.y; X2.y = -X2.y; X3.y = -X3.y; }
+                float2 a1, b1, a2, b2;
+                if (pass == 0) { a1 = phat(X0, X1); b1 = phat(X0, X2); a2 = phat(X0, X3); b2 = phat(X1, X2); }
+                else           { a1 = phat(X1, X3); b1 = phat(X2, X3); a2 = make_float2(0.f, 0.f); b2 = a2; }
+                re[m] = make_float2(a1.x - b1.y, a2.x - b2.y);
+                im[m] = make_float2(a1.y + b1.x, a2.y + b2.x);
+            });
+            // inverse 32-point stage over m: swap(FFT(swap(z)))
+            fft32(im, re);                                                  // position p: A[lane][n2 = brev5(p)]
+            static_for<1, 32>([&](auto pi) {
+                constexpr int p = decltype(pi)::value;
+                constexpr int n2 = brev5(p);
+                const float2 w = tw_s[n2 * 32 + lane];                      // (cos, -sin): multiply by (cos + i sin)
+                const float2 r = re[p], i = im[p];
+                re[p] = vfmas(i, w.y, vmuls(r, w.x));
+                im[p] = vfmas(i, w.x, vmuls(r, -w.y));
+            });
+            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = re[p]; });
+            __syncwarp();
+            static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; re[j] = scratch[lane * 33 + j]; });
+            __syncwarp();
+            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = im[p]; });
+            __syncwarp();
+            static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; im[j] = scratch[lane * 33 + j]; });
+            __syncwarp();
+            // second stage, only n1 = 0 (lag n2 = lane) and n1 = 31 (lag lane - 32):
+            //   c0 = sum_k1 A'[k1],  c31 = sum_k1 A'[k1] * (cos(2 pi k1/32) - i sin(2 pi k1/32))
+            float2 c0r = re[0], c0i = im[0], c31r = re[0], c31i = im[0];
+            static_for<1, 32>([&](auto ki) {
+                constexpr int k1 = decltype(ki)::value;
+                constexpr float c = (float)(k1 <= 16 ? cos32(k1) : cos32(32 - k1));
+                constexpr float s = (float)(k1 <= 16 ? sin32(k1) : -sin32(32 - k1));
+                c0r = vadd(c0r, re[k1]); c0i = vadd(c0i, im[k1]);
+                c31r = vfmas(im[k1], s, vfmas(re[k1], c, c31r));            // Re += r c + i s
+                c31i = vfmas(re[k1], -s, vfmas(im[k1], c, c31i));           // Im += i c - r s
+            });
+            constexpr float kInvN = 1.0f / 1024.0f;
+            // real part = first pair of the job, imaginary part = second pair
+            float* g = ob + (int64_t)(4 + 4 * pass) * ch_stride;
+            g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;
+            g[1 * ch_stride + lane] = c31i.x * kInvN;  g[1 * ch_stride + 32 + lane] = c0i.x * kInvN;
+            if (pass == 0) {
+                g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;
+                g[3 * ch_stride + lane] = c31i.y * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.y * kInvN;
+            }
+        }
+    }
+    flush_max();
+}
+
+// top_db floor of the log-mel planes: v = max(v, max_over_plane - top_db)
+__global__ void mic_topdb_kernel(float* __restrict__ out, const int* __restrict__ maxkey, int B, int Cout,
+                                 int64_t plane, float top_db) {
+    const int bc = blockIdx.y;                                             // b * 4 + c
+    const int b = bc >> 2, c = bc & 3;
+    const int key = maxkey[bc];
+    const float mx = __int_as_float(key >= 0 ? key : key ^ 0x7fffffff);
+    const float floor_db = mx - top_db;
+    float4* p = reinterpret_cast<float4*>(out + ((int64_t)b * Cout + c) * plane);
+    const int64_t n4 = plane >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = p[i];
+        v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db); v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+        p[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+static size_t mic_smem_bytes(const PlanDev& pd) {
+    return (size_t)(2 * 1024 + 1024 + 32 * melseg::kWabStride + pd.gseg_pad + mic::kW * mic::kRegion) * sizeof(float);
+}
+
+bool mic_supported(const PlanDev& pd, size_t smem_optin) {
+    return pd.fast_ok && pd.n_mels == 64 && mic_smem_bytes(pd) <= smem_optin;
+}
+
+int mic_frames_per_tile() { return mic::kW; }
+
+cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float top_db, bool use_top_db,
+                       int sm_count, cudaStream_t st) {
+    const size_t smem = mic_smem_bytes(pd);
+    cudaError_t e = cudaFuncSetAttribute(mic_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(maxkey, 0x80, (size_t)a.B * 4 * sizeof(int), st);  // key 0x80808080: below any dB value
+    if (e != cudaSuccess) return e;
+    int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
+    mic_features_kernel<<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !use_top_db) return e;
+    const int64_t plane = (int64_t)a.T * pd.n_mels;                         // multiple of 4 (n_mels = 64)
+    dim3 grid((unsigned)((plane / 4 + 255) / 256 > 64 ? 64 : (plane / 4 + 255) / 256), (unsigned)(a.B * 4));
+    mic_topdb_kernel<<<grid, 256, 0, st>>>(a.out, maxkey, a.B, a.Cout, plane, top_db);
+    return cudaGetLastError();
+}
+
+}  // namespace seld

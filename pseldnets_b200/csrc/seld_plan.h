@@ -56,4 +56,11 @@ bool foa_iv3_supported(const PlanDev& pd, size_t smem_optin);
 int foa_iv3_frames_per_tile();
 cudaError_t foa_iv3_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
 
+
+// MIC kernel: log-mel + GCC-PHAT of 4 microphones (seld_mic.cu)
+bool mic_supported(const PlanDev& pd, size_t smem_optin);
+int mic_frames_per_tile();
+cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float top_db, bool use_top_db,
+                       int sm_count, cudaStream_t st);
+
 }  // namespace seld

@@ -17,7 +17,8 @@ import torch
 import torch.nn as nn
 
 from . import _abi
-from .filterbank import make_window, melscale_fbanks_htk_slaney, window_fn_dict  # noqa: F401
+from .filterbank import (librosa_mel_bank, make_window, melscale_fbanks_htk_slaney,  # noqa: F401
+                         window_fn_dict)
 
 eps = torch.finfo(torch.float32).eps  # feature.py:8
 AMIN = 1e-10                          # torchaudio AmplitudeToDB
@@ -69,9 +70,13 @@ class _ExtractorBase(nn.Module):
         self.n_mels = int(data['n_mels'])
         self.sample_rate = data['sample_rate']
         self.stft_extractor = _Buffer('window', make_window(data['window'], self.n_fft))
-        self.mel_scale = _Buffer('fb', melscale_fbanks_htk_slaney(
-            self.n_fft // 2 + 1, 20, self.sample_rate / 2, self.n_mels, self.sample_rate))
+        self.mel_scale = _Buffer('fb', self._make_bank())
         self._plans = {}
+
+    def _make_bank(self):
+        # MelScale(norm='slaney', f_min=20, f_max=sr/2, mel_scale='htk' default) -- feature.py:32-34
+        return melscale_fbanks_htk_slaney(self.n_fft // 2 + 1, 20, self.sample_rate / 2, self.n_mels,
+                                          self.sample_rate)
 
     def _plan(self, device):
         win, fb = self.stft_extractor.window, self.mel_scale.fb
@@ -124,3 +129,65 @@ class Logmel_Extractor(_ExtractorBase):
     """log-mel of every channel.  feature.py:59-91."""
     _entry = 'seld_logmel_f32'
     _extra_ch = 0
+
+
+class LogmelGCC_Extractor(_ExtractorBase):
+    """MIC-format features as an nn.Module (the reference only has the numpy/librosa class
+    `Features_Extractor_MIC`, feature.py:119-175, driven by preprocess.py:546-556):
+    x (B, 4, L) -> (B, 4 + 6, int(L/hop), n_mels): per-mic log-mel (librosa Slaney bank,
+    power_to_db with top_db=80 per plane) + GCC-PHAT of the 6 mic pairs, lags [-n_mels/2, n_mels/2).
+    `mel_scale.fb` holds `librosa.filters.mel(sr, n_fft, n_mels).T`."""
+    _entry = 'seld_logmel_gcc_f32'
+    top_db = 80.0            # librosa.power_to_db default
+
+    def _make_bank(self):
+        return librosa_mel_bank(self.sample_rate, self.n_fft, self.n_mels)      # feature.py:126
+
+    def forward(self, x):
+        if x.ndim != 3:
+            raise ValueError("x shape must be (batch_size, num_channels, data_length)\n \
+                            Now it is {}".format(x.shape))
+        if not x.is_cuda:
+            raise RuntimeError('pseldnets_b200 extractors run on CUDA tensors only (no CPU path); '
+                               'got a tensor on %s' % x.device)
+        if x.dtype != torch.float32:
+            raise TypeError('expected float32 waveform, got %s' % x.dtype)
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        B, C, L = x.shape
+        dev = x.device
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        plan = self._plan(dev)
+        lib = _abi.lib()
+        T = L // self.hop
+        out = torch.empty((B, C + C * (C - 1) // 2, T, self.n_mels), dtype=torch.float32, device=x.device)
+        ws = torch.empty((max(1, lib.seld_workspace_bytes(plan.handle, B, C) // 4),), dtype=torch.int32,
+                         device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        top_db = -1.0 if self.top_db is None else float(self.top_db)
+        code = lib.seld_logmel_gcc_f32(plan.handle, x.data_ptr(), B, C, L, x.stride(0), x.stride(1), top_db,
+                                       out.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+        _abi.check(code, self._entry)
+        return out
+
+
+class Features_Extractor_MIC():
+    """Name-compatible front for the reference's MIC class (feature.py:119-175).  The fused kernel
+    never materialises the complex spectrogram, so instead of the three numpy stages
+    (_spectrogram -> _get_logmel_spectrogram / _get_gcc) it exposes their composition as used by
+    Preprocess.extract_mic_features (preprocess.py:546-556): (L, C) float32 audio in soundfile
+    layout -> (C + C(C-1)/2, T, n_mels) float32 numpy feature."""
+
+    def __init__(self, cfg, device='cuda'):
+        self.fs = cfg['data']['sample_rate']
+        self.n_fft = cfg['data']['nfft']
+        self.n_mels = cfg['data']['n_mels']
+        self.hoplen = cfg['data']['hoplen']
+        self.window = cfg['data']['window']
+        self._ext = LogmelGCC_Extractor(cfg).to(device)
+        self.mel_bank = self._ext.mel_scale.fb.cpu().numpy()
+
+    def extract_logmelgcc(self, waveform):
+        x = torch.as_tensor(waveform, dtype=torch.float32).t().unsqueeze(0)        # (1, C, L)
+        return self._ext(x.to(self._ext.mel_scale.fb.device))[0].cpu().numpy()

@@ -1,0 +1,122 @@
+"""GPU: MIC path (log-mel + GCC-PHAT) through LogmelGCC_Extractor -> C ABI -> CUDA against the
+numpy oracle (oracle/seld_oracle.py:logmel_gcc -- a restatement of the reference's librosa/numpy
+class; "parity unpinned": librosa is not installable offline).  Tolerances (north_star): log-mel
+1e-4 of the block maximum, GCC-PHAT 1e-4 absolute."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import block_err, make_cfg
+import pseldnets_b200 as pb
+from pseldnets_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _mic(sr=24000, hop=240):
+    return pb.get_afextractor(make_cfg(sr, hop, 'hann', 'logmelgcc')).cuda()
+
+
+def _oracle(ext, x, dtype=np.float64, top_db=80.0):
+    from oracle import seld_oracle as so
+    return so.logmel_gcc(x, ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy(),
+                         1024, ext.hop, top_db=top_db, dtype=dtype)
+
+
+def _check(y, ref, what):
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    assert np.isfinite(y).all()
+    e = block_err(y, ref, slice(0, 4))
+    assert e <= 1e-4, '%s: log-mel block error %.3e' % (what, e)
+    g = float(np.abs(y[:, 4:].astype(np.float64) - ref[:, 4:]).max())
+    assert g <= 1e-4, '%s: GCC abs error %.3e' % (what, g)
+
+
+def test_mic_against_oracle_small_and_ragged():
+    from oracle import synth
+    ext = _mic()
+    for seed, B, L in ((31, 2, 4800), (32, 1, 5003), (33, 3, 1200)):
+        x = synth.white(seed, B, 4, L)
+        y = ext(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert y.shape == (B, 10, L // 240, 64)
+        _check(y, _oracle(ext, x), 'L=%d' % L)
+
+
+def test_mic_32k():
+    from oracle import synth
+    ext = _mic(32000, 320)
+    x = synth.white(34, 2, 4, 9600)
+    _check(ext(torch.from_numpy(x).cuda()).cpu().numpy(), _oracle(ext, x), 'sr=32k')
+
+
+def test_mic_pure_delay_peaks_at_lag():
+    from oracle import synth
+    ext = _mic()
+    s = synth.white(35, 1, 1, 24000 + 32)[0, 0]
+    d = 7
+    x = np.stack([s[16:16 + 24000], s[16 - d:16 - d + 24000], s[16 + 3:16 + 3 + 24000], s[16:16 + 24000]])[None]
+    y = ext(torch.from_numpy(np.ascontiguousarray(x)).cuda()).cpu().numpy()
+    mid = y[0, :, 50]
+    assert int(np.argmax(mid[4])) == 32 + d          # pair (0,1): mic1 lags mic0 by d
+    assert int(np.argmax(mid[5])) == 32 - 3          # pair (0,2): mic2 leads by 3
+    assert int(np.argmax(mid[6])) == 32              # pair (0,3): identical
+    _check(y, _oracle(ext, x), 'delay')
+
+
+def test_mic_top_db_floor_and_disable():
+    from oracle import synth
+    ext = _mic()
+    x = synth.white(36, 2, 4, 9600)
+    x[:, :, 4800:] *= 1e-6                            # 120 dB quieter tail -> floor at max - 80 dB
+    xt = torch.from_numpy(x).cuda()
+    y = ext(xt).cpu().numpy()
+    ref = _oracle(ext, x)
+    _check(y, ref, 'top_db=80')
+    for b in range(2):
+        for c in range(4):
+            assert abs(y[b, c].min() - (y[b, c].max() - 80.0)) < 1e-3
+    ext.top_db = None
+    y2 = ext(xt).cpu().numpy()
+    _check(y2, _oracle(ext, x, top_db=None), 'top_db=None')
+    assert y2[:, :4].min() < y[:, :4].min() - 10.0     # without the floor the quiet tail sits at the amin clamp
+
+
+def test_mic_silence_and_errors():
+    ext = _mic()
+    y = ext(torch.zeros(1, 4, 2400, device='cuda')).cpu().numpy()
+    assert np.abs(y[:, :4] + 100.0).max() < 1e-4
+    # phasor of 0 is 1 -> irfft of all-ones = delta at lag 0 (column 32)
+    g = y[0, 4:, 5]
+    assert np.abs(g[:, 32] - 1.0).max() < 1e-5 and np.abs(np.delete(g, 32, axis=1)).max() < 1e-5
+    with pytest.raises(_abi.SeldError):
+        ext(torch.zeros(1, 3, 2400, device='cuda'))
+    with pytest.raises(ValueError):
+        ext(torch.zeros(4, 2400, device='cuda'))
+    assert ext(torch.zeros(0, 4, 2400, device='cuda')).shape == (0, 10, 10, 64)
+    assert ext(torch.zeros(2, 4, 100, device='cuda')).shape == (2, 10, 0, 64)
+
+
+def test_mic_numpy_front():
+    from oracle import synth
+    cfg = make_cfg(24000, 240, 'hann', 'logmelgcc')
+    front = pb.Features_Extractor_MIC(cfg)
+    audio = synth.white(37, 1, 4, 4800)[0].T.copy()             # (L, C) soundfile layout
+    feat = front.extract_logmelgcc(audio)
+    assert feat.shape == (10, 20, 64) and feat.dtype == np.float32
+    _check(feat[None], _oracle(front._ext, audio.T[None]), 'numpy front')
+
+
+def test_mic_cfg3_full_size():
+    """BASELINE cfg3: B=64 x 10 s x 4 mics -> (64, 10, 1000, 64); clips 0-1 against the oracle,
+    batch independence and gain invariance of GCC at full size."""
+    ext = _mic()
+    g = torch.Generator(device='cuda').manual_seed(1235)
+    x = 0.1 * torch.randn(64, 4, 240000, device='cuda', generator=g)
+    y = ext(x)
+    assert y.shape == (64, 10, 1000, 64) and torch.isfinite(y).all()
+    for b in (0, 40, 63):
+        assert torch.equal(ext(x[b:b + 1]), y[b:b + 1])
+    y3 = ext(3.0 * x[:2])
+    assert (y3[:, 4:] - y[:2, 4:]).abs().max().item() < 1e-4
+    assert (y3[:, :4] - y[:2, :4] - 20.0 * np.log10(3.0)).abs().max().item() < 1e-4 * y[:2, :4].abs().max().item()
+    _check(y[:2].cpu().numpy(), _oracle(ext, x[:2].cpu().numpy()), 'cfg3 clips 0-1')
