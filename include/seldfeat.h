@@ -49,6 +49,16 @@ int64_t seld_num_frames(const seld_plan* plan, int64_t L);
 int seld_logmel_iv_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
                        int64_t stride_b, int64_t stride_c, float* out, void* stream);
 
+/* Same computation with HOST buffers: x_host (B, C, L) contiguous and out_host (B, C+3, T, n_mels)
+ * contiguous, ideally page-locked.  The batch is cut into chunks of `chunk_clips` clips (<= 0:
+ * library default) that flow through three plan-owned device slots on three internal streams, so
+ * the host->device copy of chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1
+ * overlap (PCIe is full duplex).  Ordered after prior work on `stream` and before later work on it;
+ * returns once everything is enqueued.  Device slots are allocated on first use and kept in the
+ * plan (this is the one compute entry point that may allocate, on its first call per size). */
+int seld_logmel_iv_f32_host(seld_plan* plan, const float* x_host, int64_t B, int C, int64_t L,
+                            float* out_host, int chunk_clips, void* stream);
+
 /* Logmel_Extractor.forward (feature.py:76-91): x (B, C>=1, L) -> out (B, C, T, n_mels). */
 int seld_logmel_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
                     int64_t stride_b, int64_t stride_c, float* out, void* stream);

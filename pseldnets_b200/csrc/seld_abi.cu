@@ -12,7 +12,18 @@
 #include "../../include/seldfeat.h"
 #include "seld_plan.h"
 
+struct HostPipe {                 // device slots + streams of seld_logmel_iv_f32_host
+    static const int kSlots = 3;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
+    float* din[kSlots] = {};
+    float* dout[kSlots] = {};
+    size_t cap_in = 0, cap_out = 0;
+    bool ready = false;
+};
+
 struct seld_plan {
+    HostPipe pipe;
     seld::PlanDev dev;
     int device;
     int sm_count;
@@ -191,8 +202,25 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     return SELD_OK;
 }
 
+static void pipe_free_slots(HostPipe& hp) {
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        if (hp.din[i]) cudaFree(hp.din[i]);
+        if (hp.dout[i]) cudaFree(hp.dout[i]);
+        hp.din[i] = hp.dout[i] = nullptr;
+    }
+    hp.cap_in = hp.cap_out = 0;
+}
+
 extern "C" void seld_plan_destroy(seld_plan* p) {
     if (!p) return;
+    HostPipe& hp = p->pipe;
+    if (hp.ready) {
+        cudaStreamSynchronize(hp.s_in); cudaStreamSynchronize(hp.s_k); cudaStreamSynchronize(hp.s_out);
+        pipe_free_slots(hp);
+        cudaStreamDestroy(hp.s_in); cudaStreamDestroy(hp.s_k); cudaStreamDestroy(hp.s_out);
+        cudaEventDestroy(hp.ev_start);
+        for (int i = 0; i < HostPipe::kSlots; ++i) { cudaEventDestroy(hp.ev_in[i]); cudaEventDestroy(hp.ev_k[i]); cudaEventDestroy(hp.ev_out[i]); }
+    }
     if (p->blob) cudaFree(p->blob);
     delete p;
 }
@@ -245,6 +273,74 @@ static int run_foa(const seld_plan* p, bool iv, const float* x, int64_t B, int C
 extern "C" int seld_logmel_iv_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,
                                   int64_t stride_b, int64_t stride_c, float* out, void* stream) {
     return run_foa(p, true, x, B, C, L, stride_b, stride_c, out, stream);
+}
+
+extern "C" int seld_logmel_iv_f32_host(seld_plan* p, const float* x_host, int64_t B, int C, int64_t L,
+                                       float* out_host, int chunk_clips, void* stream) {
+    if (!p || B < 0 || C < 4 || L < 1) return SELD_EINVAL;
+    if (L <= p->n_fft / 2) return SELD_ESHORT;
+    if (B == 0) return SELD_OK;
+    if (!x_host || !out_host) return SELD_EINVAL;
+    const int64_t T = 1 + L / p->dev.hop;
+    const int64_t in_clip = (int64_t)C * L, out_clip = (int64_t)(C + 3) * T * p->dev.n_mels;
+    int64_t cc = chunk_clips > 0 ? chunk_clips : 8;
+    if (cc > B) cc = B;
+    HostPipe& hp = p->pipe;
+    int prev = 0;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e == cudaSuccess) e = cudaSetDevice(p->device);
+    if (e != cudaSuccess) return cuda_fail(e);
+#define SELD_TRY(call) do { e = (call); if (e != cudaSuccess) { cudaSetDevice(prev); return cuda_fail(e); } } while (0)
+    if (!hp.ready) {
+        SELD_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+        SELD_TRY(cudaStreamCreateWithFlags(&hp.s_k, cudaStreamNonBlocking));
+        SELD_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+        SELD_TRY(cudaEventCreateWithFlags(&hp.ev_start, cudaEventDisableTiming));
+        for (int i = 0; i < HostPipe::kSlots; ++i) {
+            SELD_TRY(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+            SELD_TRY(cudaEventCreateWithFlags(&hp.ev_k[i], cudaEventDisableTiming));
+            SELD_TRY(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+        }
+        hp.ready = true;
+    }
+    const size_t need_in = (size_t)(cc * in_clip) * 4, need_out = (size_t)(cc * out_clip) * 4;
+    if (need_in > hp.cap_in || need_out > hp.cap_out) {
+        SELD_TRY(cudaStreamSynchronize(hp.s_in)); SELD_TRY(cudaStreamSynchronize(hp.s_k)); SELD_TRY(cudaStreamSynchronize(hp.s_out));
+        pipe_free_slots(hp);
+        for (int i = 0; i < HostPipe::kSlots; ++i) {
+            SELD_TRY(cudaMalloc(&hp.din[i], need_in));
+            SELD_TRY(cudaMalloc(&hp.dout[i], need_out));
+        }
+        hp.cap_in = need_in; hp.cap_out = need_out;
+    }
+    cudaStream_t user = (cudaStream_t)stream;
+    SELD_TRY(cudaEventRecord(hp.ev_start, user));
+    SELD_TRY(cudaStreamWaitEvent(hp.s_in, hp.ev_start, 0));
+    SELD_TRY(cudaStreamWaitEvent(hp.s_k, hp.ev_start, 0));
+    SELD_TRY(cudaStreamWaitEvent(hp.s_out, hp.ev_start, 0));
+    int n = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += cc, ++n) {
+        const int64_t nb = (B - b0 < cc) ? (B - b0) : cc;
+        const int sl = n % HostPipe::kSlots;
+        if (n >= HostPipe::kSlots) {                 // slot reuse: its previous kernel / copy-out must be done
+            SELD_TRY(cudaStreamWaitEvent(hp.s_in, hp.ev_k[sl], 0));
+            SELD_TRY(cudaStreamWaitEvent(hp.s_k, hp.ev_out[sl], 0));
+        }
+        SELD_TRY(cudaMemcpyAsync(hp.din[sl], x_host + b0 * in_clip, (size_t)(nb * in_clip) * 4, cudaMemcpyHostToDevice, hp.s_in));
+        SELD_TRY(cudaEventRecord(hp.ev_in[sl], hp.s_in));
+        SELD_TRY(cudaStreamWaitEvent(hp.s_k, hp.ev_in[sl], 0));
+        const int rc = run_foa(p, true, hp.din[sl], nb, C, L, in_clip, L, hp.dout[sl], hp.s_k);
+        if (rc != SELD_OK) { cudaSetDevice(prev); return rc; }
+        SELD_TRY(cudaEventRecord(hp.ev_k[sl], hp.s_k));
+        SELD_TRY(cudaStreamWaitEvent(hp.s_out, hp.ev_k[sl], 0));
+        SELD_TRY(cudaMemcpyAsync(out_host + b0 * out_clip, hp.dout[sl], (size_t)(nb * out_clip) * 4, cudaMemcpyDeviceToHost, hp.s_out));
+        SELD_TRY(cudaEventRecord(hp.ev_out[sl], hp.s_out));
+    }
+    // later work on the caller's stream sees the finished batch
+    for (int i = 0; i < HostPipe::kSlots && i < n; ++i) SELD_TRY(cudaStreamWaitEvent(user, hp.ev_out[i], 0));
+#undef SELD_TRY
+    cudaSetDevice(prev);
+    return SELD_OK;
 }
 
 extern "C" int seld_logmel_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,

@@ -125,6 +125,33 @@ class LogmelIV_Extractor(_ExtractorBase):
     _extra_ch = 3
 
 
+    def forward_host(self, x, out=None, device=None, chunk_clips=0):
+        """Host-buffer form of forward(): x is a CPU float32 tensor (B, C, L) (page-locked for
+        full overlap); returns a page-locked CPU tensor (B, C+3, T, n_mels).  Chunks of the batch
+        are copied in, transformed and copied out on three overlapping streams inside
+        libseldfeat.so (seld_logmel_iv_f32_host).  The result is complete once the current stream
+        of `device` has been synchronised."""
+        if x.ndim != 3:
+            raise ValueError("x shape must be (batch_size, num_channels, data_length)\n \
+                            Now it is {}".format(x.shape))
+        if x.is_cuda or x.dtype != torch.float32:
+            raise TypeError('forward_host expects a CPU float32 tensor')
+        x = x.contiguous()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        B, C, L = x.shape
+        T = 1 + L // self.hop
+        if out is None:
+            out = torch.empty((B, C + 3, T, self.n_mels), dtype=torch.float32, pin_memory=True)
+        plan = self._plan(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        code = _abi.lib().seld_logmel_iv_f32_host(plan.handle, x.data_ptr(), B, C, L, out.data_ptr(),
+                                                  int(chunk_clips), stream)
+        _abi.check(code, 'seld_logmel_iv_f32_host')
+        return out
+
+
 class Logmel_Extractor(_ExtractorBase):
     """log-mel of every channel.  feature.py:59-91."""
     _entry = 'seld_logmel_f32'

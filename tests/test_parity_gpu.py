@@ -197,3 +197,20 @@ def test_full_size_properties_cfg2():
     ref = so.logmel_iv(x[:4].cpu().numpy(), ext.stft_extractor.window.cpu().numpy(),
                        ext.mel_scale.fb.cpu().numpy(), 1024, 240, np.float64)
     assert_blocks_close(y[:4].cpu().numpy(), ref, 4, what='cfg2 clips 0-3')
+
+
+def test_host_buffer_entry_matches_resident_path():
+    """seld_logmel_iv_f32_host (chunked H2D / kernel / D2H pipeline) returns the same bits."""
+    from oracle import synth
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    x = torch.from_numpy(synth.white(600, 11, 4, 24000))
+    ref = ext(x.cuda()).cpu()
+    for chunk in (0, 1, 3, 4, 16):
+        y = ext.forward_host(x.pin_memory(), chunk_clips=chunk)
+        torch.cuda.synchronize()
+        assert y.is_pinned() and torch.equal(y, ref), chunk
+    y = ext.forward_host(x)                          # pageable input also works (copies just do not overlap)
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
+    with pytest.raises(ValueError):
+        ext.forward_host(torch.zeros(4, 2400))
