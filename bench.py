@@ -145,6 +145,71 @@ def run_reference(args):
     }))
 
 
+def run_extra(args):
+    """cfg3 / cfg4 of BASELINE.json: resident-input throughput + roofline of the extra workloads."""
+    import torch
+    import torch.distributed as dist
+    import pseldnets_b200 as pb
+    from pseldnets_b200 import _abi, shard
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if args.workload == 'cfg3':
+        sr, hop, Lw, Cin, name = 24000, 240, 240000, 4, 'cfg3: MIC log-mel+GCC-PHAT, batch 64 x 10 s x 4 mics @ 24 kHz per GPU -> (64,10,1000,64)'
+        ext = pb.get_afextractor({'data': dict(CFG['data'], audio_feature='logmelgcc')}).to(dev)
+        nb = 64
+        step = lambda x: ext(x)
+        out_bytes = 10 * 1000 * 64 * 4
+        scaling = 'weak'
+    else:
+        sr, hop, Lw, Cin, name = 32000, 320, 320000, 8, 'cfg4: L3DAS22 dual-FOA 8 ch @ 32 kHz, global batch 128 x 10 s sharded by clip -> (128,14,1001,64)'
+        ext = pb.get_afextractor({'data': dict(CFG['data'], sample_rate=sr, hoplen=hop)}).to(dev)
+        a, b = shard.clip_shard(128, rank, world)
+        nb = b - a
+        # two FOA arrays per clip: view (nb, 8, L) as (2 nb, 4, L) -> (2 nb, 7, T, 64) == (nb, 14, T, 64)
+        step = lambda x: ext(x.view(2 * x.shape[0], 4, x.shape[2])).view(x.shape[0], 14, 1001, 64)
+        out_bytes = 14 * 1001 * 64 * 4
+        scaling = 'strong'
+    g = torch.Generator(device=dev).manual_seed(1235 + rank)
+    x = 0.1 * torch.randn(nb, Cin, Lw, device=dev, generator=g)
+    for _ in range(max(args.warmup, 3)):
+        y = step(x)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _abi.lib().seld_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        y = step(x)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.steps
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        n_global = nb * world if args.workload == 'cfg3' else 128
+        algo = nb * (Cin * Lw * 4 + out_bytes)
+        print(json.dumps({'metric': 'audio-seconds/sec (%s)' % args.workload, 'value': n_global * CLIP_S / (ms * 1e-3), 'unit': UNIT,
+                          'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
+                          'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': name},
+                          'roofline': {'bound': 'hbm', 'achieved': algo / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                       'frac': algo / (ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                                       'algorithmic_bytes_per_step_per_gpu': algo},
+                          'gpu_launches': int(_abi.lib().seld_launch_count() - l0), 'outputs_finite': bool(torch.isfinite(y).all())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -267,10 +332,15 @@ def main():
     ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='clips per GPU per step (cfg2: 64)')
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'],
+                    help='cfg2 = BASELINE metric (default); cfg3 = MIC log-mel+GCC B=64; cfg4 = L3DAS22 dual-FOA '
+                         '8 ch 32 kHz, global batch 128 sharded by clip (extra measurements, not the headline)')
     ap.add_argument('--cpu-seconds', type=float, default=10.0, help='bound on the cpu_baseline sample')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload != 'cfg2':
+        run_extra(args)
     else:
         run_ours(args)
 

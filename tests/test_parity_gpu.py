@@ -214,3 +214,37 @@ def test_host_buffer_entry_matches_resident_path():
     assert torch.equal(y, ref)
     with pytest.raises(ValueError):
         ext.forward_host(torch.zeros(4, 2400))
+
+
+def test_cfg4_l3das22_dual_foa():
+    """BASELINE cfg4 semantics: an 8-channel 32 kHz clip is two FOA arrays; viewed as
+    (2B, 4, L) the extractor yields (B, 14, T, 64) = 2 x [4 log-mel + 3 IV]."""
+    from oracle import seld_oracle as so
+    ext = _ext('logmelIV', 32000, 320, 'hann')
+    g = torch.Generator(device='cuda').manual_seed(1236)
+    x = 0.1 * torch.randn(16, 8, 320000, device='cuda', generator=g)
+    y = ext(x.view(32, 4, 320000)).view(16, 14, 1001, 64)
+    assert torch.isfinite(y).all()
+    # array B of clip 3 alone gives the same bits as its slice of the batched call
+    assert torch.equal(ext(x[3:4, 4:8].contiguous())[0], y[3, 7:14])
+    ref = so.logmel_iv(x[:1].view(2, 4, 320000).cpu().numpy(), ext.stft_extractor.window.cpu().numpy(),
+                       ext.mel_scale.fb.cpu().numpy(), 1024, 320, np.float64)
+    assert_blocks_close(y[:1].view(2, 7, 1001, 64).cpu().numpy(), ref, 4, what='cfg4 clip 0')
+
+
+def test_cfg5_epoch_sweep_scaled():
+    """cfg5 (67k one-minute clips = 402k ten-second chunks) scaled to one minute-long clip set:
+    chunking a long recording and extracting chunk by chunk equals extracting the chunks as a batch,
+    and the per-clip checksums are stable over repeated sweeps of a resident pool."""
+    from pseldnets_b200 import shard
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    g = torch.Generator(device='cuda').manual_seed(1237)
+    minute = 0.1 * torch.randn(4, 4, 1440000, device='cuda', generator=g)          # 4 one-minute clips
+    chunks = minute.view(4, 4, 6, 240000).permute(0, 2, 1, 3).reshape(24, 4, 240000)   # preprocess.py:464-521 chunking
+    full = ext(chunks)
+    ref = shard.clip_checksums(full)
+    for sweep in range(3):
+        parts = [ext(chunks[i:i + 8]) for i in range(0, 24, 8)]
+        assert torch.equal(torch.cat(parts), full), sweep                  # features: bit-identical
+        got = torch.cat([shard.clip_checksums(p) for p in parts])
+        assert torch.allclose(got, ref, rtol=1e-12, atol=0), sweep         # fp64 reductions: order may differ
