@@ -13,8 +13,8 @@
 //      maximum is kept in registers and flushed with one atomicMax per clip change;
 //   4. GCC-PHAT: two passes of two packed inverse transforms.  A transform's input is
 //      Z = ph_a + i*ph_b for two mic pairs (its real/imag outputs are the two correlations); lane l
-//      builds Z[l + 32m] for all m from the shared spectra (bins above 512 are the conjugates of
-//      1024-k), runs the 32-point inverse stage in registers, twiddles, exchanges, and -- because
+//      builds Z[l + 32m] for all m from the shared unit phasors X_c/|X_c| (bins above 512 are the
+//      conjugates of 1024-k), runs the 32-point inverse stage in registers, twiddles, exchanges, and -- because
 //      only lags [-32, 32) are kept -- evaluates just the two needed outputs of the second stage.
 // A second, element-wise kernel applies the top_db floor once every frame's maximum is known.
 #include <cuda_runtime.h>
@@ -37,20 +37,15 @@ constexpr int kRegion = kSpec + kRowsArea;
 // order-preserving float <-> int key for atomicMax
 __device__ __forceinline__ int f2key(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
 
-// unit phasor of conj(a) * b; 1 when the product vanishes (np.angle(0) = 0)
-__device__ __forceinline__ float2 phat(float2 a, float2 b) {
-    const float re = fmaf(a.y, b.y, a.x * b.x), im = fmaf(-a.y, b.x, a.x * b.y);
-    const float s = fmaf(im, im, re * re);
-    if (!(s > 1e-37f)) {
-        // rescale tiny products before normalising (keeps the phase of quiet bins)
-        const float m = fmaxf(fabsf(re), fabsf(im));
-        if (m == 0.0f) return make_float2(1.0f, 0.0f);
-        const float r2 = re / m, i2 = im / m;
-        const float inv = rsqrtf(fmaf(i2, i2, r2 * r2));
-        return make_float2(r2 * inv, i2 * inv);
-    }
-    const float inv = rsqrt_ftz(s);
-    return make_float2(re * inv, im * inv);
+// X / |X| given |X|^2 (0 for a vanishing bin, so that products with it vanish too)
+__device__ __forceinline__ float inv_mag(float p) { return p > 1e-37f ? rsqrt_ftz(p) : 0.0f; }
+
+// conj(ua) * ub for unit (or zero) phasors; a vanishing product means angle(0) = 0 -> phasor 1
+__device__ __forceinline__ float2 cross_phasor(float2 ua, float2 ub) {
+    float re = fmaf(ua.y, ub.y, ua.x * ub.x);
+    const float im = fmaf(-ua.y, ub.x, ua.x * ub.y);
+    if (re == 0.0f && im == 0.0f) re = 1.0f;
+    return make_float2(re, im);
 }
 }  // namespace mic
 
@@ -176,10 +171,12 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             const float2 p13 = __ffma2_rn(bi, bi, __fmul2_rn(br, br));
             if (kb < 16 || lane == 0) {
                 const int k = lane + 32 * kb;
-                spec[0 * kSpecStride + k] = make_float2(ar.x, ai.x);
-                spec[1 * kSpecStride + k] = make_float2(br.x, bi.x);
-                spec[2 * kSpecStride + k] = make_float2(ar.y, ai.y);
-                spec[3 * kSpecStride + k] = make_float2(br.y, bi.y);
+                // PHAT only needs phases: keep X_c / |X_c| (unit phasors) for the GCC passes
+                const float n0 = inv_mag(p02.x), n1 = inv_mag(p13.x), n2 = inv_mag(p02.y), n3 = inv_mag(p13.y);
+                spec[0 * kSpecStride + k] = make_float2(ar.x * n0, ai.x * n0);
+                spec[1 * kSpecStride + k] = make_float2(br.x * n1, bi.x * n1);
+                spec[2 * kSpecStride + k] = make_float2(ar.y * n2, ai.y * n2);
+                spec[3 * kSpecStride + k] = make_float2(br.y * n3, bi.y * n3);
                 float* q = R + 32 * kb + wofs[kb & 3];
                 q[0 * kRowWords] = p02.x;
                 q[1 * kRowWords] = p13.x;
@@ -218,20 +215,25 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         }
 
         // ---------------- GCC-PHAT: pass 0 = pairs (01,02 | 03,12), pass 1 = pairs (13,23 | -, -)
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
+        auto gcc_pass = [&](auto pass_c) {
+            constexpr int pass = decltype(pass_c)::value;
             // Z1 = ph(a1) + i ph(b1) in .x halves, Z2 = ph(a2) + i ph(b2) in .y halves
             static_for<0, 32>([&](auto mi) {
                 constexpr int m = decltype(mi)::value;
                 const int k = lane + 32 * m;
                 const bool up = k > 512;
                 const int kk = up ? 1024 - k : k;
-                float2 X0 = spec[0 * kSpecStride + kk], X1 = spec[1 * kSpecStride + kk];
-                float2 X2 = spec[2 * kSpecStride + kk], X3 = spec[3 * kSpecStride + kk];
-                if (up) { X0.y = -X0.y; X1.y = -X1.y; X2.y = -X2.y; X3.y = -X3.y; }
+                const float sg = up ? -1.0f : 1.0f;                       // bins above 512: conj(u[1024-k])
                 float2 a1, b1, a2, b2;
-                if (pass == 0) { a1 = phat(X0, X1); b1 = phat(X0, X2); a2 = phat(X0, X3); b2 = phat(X1, X2); }
-                else           { a1 = phat(X1, X3); b1 = phat(X2, X3); a2 = make_float2(0.f, 0.f); b2 = a2; }
+                float2 u1 = spec[1 * kSpecStride + kk], u2 = spec[2 * kSpecStride + kk], u3 = spec[3 * kSpecStride + kk];
+                u1.y *= sg; u2.y *= sg; u3.y *= sg;
+                if constexpr (pass == 0) {
+                    float2 u0 = spec[0 * kSpecStride + kk];
+                    u0.y *= sg;
+                    a1 = cross_phasor(u0, u1); b1 = cross_phasor(u0, u2); a2 = cross_phasor(u0, u3); b2 = cross_phasor(u1, u2);
+                } else {
+                    a1 = cross_phasor(u1, u3); b1 = cross_phasor(u2, u3); a2 = make_float2(0.f, 0.f); b2 = a2;
+                }
                 re[m] = make_float2(a1.x - b1.y, a2.x - b2.y);
                 im[m] = make_float2(a1.y + b1.x, a2.y + b2.x);
             });
@@ -269,11 +271,13 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             float* g = ob + (int64_t)(4 + 4 * pass) * ch_stride;
             g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;
             g[1 * ch_stride + lane] = c31i.x * kInvN;  g[1 * ch_stride + 32 + lane] = c0i.x * kInvN;
-            if (pass == 0) {
+            if constexpr (pass == 0) {
                 g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;
                 g[3 * ch_stride + lane] = c31i.y * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.y * kInvN;
             }
-        }
+        };
+        gcc_pass(std::integral_constant<int, 0>{});
+        gcc_pass(std::integral_constant<int, 1>{});
     }
     flush_max();
 }
