@@ -100,12 +100,14 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                 wab[c * 36 + 2 * j + 1] = sk < n_mels ? fb_host[(size_t)k * n_mels + sk] : 0.0f;
             }
             const int nruns = g + 1;
-            if (2 * nruns > 512) fast_ok = 0;        // partial sums live in the first words of a row
+            if (nruns > 127) fast_ok = 0;            // partial sums live in the first 254 words of a row; slot 127 stays zero
             for (int sgm = 0; sgm <= n_mels + 1; ++sgm) {
                 int n = 0;
                 for (int r = 0; r < nruns; ++r) if (run_seg[r] < sgm) ++n;
                 gseg[sgm] = n;
             }
+            for (int sgm = 0; sgm <= n_mels; ++sgm)
+                if (gseg[sgm + 1] - gseg[sgm] > 4) fast_ok = 0;   // the combine step reads <= 4 runs per segment
         }
     }
     const int gseg_pad = (n_mels + 2 + 3) & ~3;

@@ -28,6 +28,7 @@ namespace seld {
 constexpr int kRowWords = 528;            // 33 chunks of 16 bins (bin 512 opens chunk 32)
 constexpr int kRows = 7;                  // P0 P1 P2 P3 n1 n2 n3
 constexpr int kRegion = kRows * kRowWords;   // floats per warp; the 32x33 float2 exchange buffer (2112) aliases it
+constexpr int kZeroRun = 127;             // float2 slot of every row kept at (0, 0) during the combine step
 constexpr int kWabStride = 36;            // floats per lane in the (a, b) weight table: 17 float2 + pad, 36*l mod 32 = 4l
 
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -65,6 +66,16 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     for (int i = 0; i < 4; ++i) rofs[i] = 16 * lane + 4 * (i ^ ((lane >> 1) & 3));
 
     const int64_t ch_stride = (int64_t)a.T * M;
+    // combine step, bands lane and lane+32: run numbers of segment m (V) and m+1 (U), four slots each
+    auto pack_runs = [&](int lo, int hi) {
+        uint32_t p = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p |= (uint32_t)(lo + i < hi ? lo + i : kZeroRun) << (8 * i);
+        return p;
+    };
+    uint32_t slotV0 = 0, slotU0 = 0, slotV1 = 0, slotU1 = 0;
+    if (lane < M) { slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]); slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]); }
+    if (lane + 32 < M) { slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]); slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]); }
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_clip;
@@ -165,7 +176,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         }
         __syncwarp();
 
-        // ---------------- mel step 1: chunk walk, per-run partial sums (U, V) left in the rows
+        // ---------------- mel step 1: chunk walk of all seven rows, per-run partial sums (U, V) left in the rows
         {
             float2 wv[17];
             const float4* wp = reinterpret_cast<const float4*>(wab_s + lane * kWabStride);
@@ -176,69 +187,89 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 wv[2 * i + 1] = make_float2(v.z, v.w);
             }
             wv[16] = *reinterpret_cast<const float2*>(wab_s + lane * kWabStride + 32);
-
-            auto walk = [&](auto f0c, auto nfc) {
-                constexpr int f0 = decltype(f0c)::value, nf = decltype(nfc)::value;
-                float q[nf][17];
+            float q[kRows][17];
 #pragma unroll
-                for (int f = 0; f < nf; ++f) {
-                    const float* row = R + (f0 + f) * kRowWords;
+            for (int f = 0; f < kRows; ++f) {
+                const float* row = R + f * kRowWords;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 v = *reinterpret_cast<const float4*>(row + rofs[i]);
-                        q[f][4 * i] = v.x; q[f][4 * i + 1] = v.y; q[f][4 * i + 2] = v.z; q[f][4 * i + 3] = v.w;
-                    }
-                    q[f][16] = lane == 31 ? row[512] : 0.0f;
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + rofs[i]);
+                    q[f][4 * i] = v.x; q[f][4 * i + 1] = v.y; q[f][4 * i + 2] = v.z; q[f][4 * i + 3] = v.w;
                 }
-                __syncwarp();                                               // everyone holds its bins: rows may be overwritten
-                float2 acc[nf];
-                float2* po = reinterpret_cast<float2*>(R + f0 * kRowWords) + g0;
+                q[f][16] = lane == 31 ? row[512] : 0.0f;
+            }
+            __syncwarp();                                                   // everyone holds its bins: rows may be overwritten
+            if (lane < kRows) reinterpret_cast<float2*>(R + lane * kRowWords)[kZeroRun] = make_float2(0.f, 0.f);
+            float2 acc[kRows];
+            float2* po = reinterpret_cast<float2*>(R) + g0;
 #pragma unroll
-                for (int f = 0; f < nf; ++f) acc[f] = vmuls(wv[0], q[f][0]);
-                static_for<1, 17>([&](auto ji) {
-                    constexpr int j = decltype(ji)::value;
-                    if ((runmask >> j) & 1u) {                              // a new run starts at this bin
+            for (int f = 0; f < kRows; ++f) acc[f] = vmuls(wv[0], q[f][0]);
+            // branch-free: where a new run starts the finished pair is stored and the accumulator restarts
+            // (acc * keep with keep = 0); one FMUL2 + one FFMA2 + one predicated store per bin and row
+            static_for<1, 17>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const bool start = (runmask >> j) & 1u;
+                const float keep = start ? 0.0f : 1.0f;
 #pragma unroll
-                        for (int f = 0; f < nf; ++f) {
-                            po[f * (kRowWords / 2)] = acc[f];
-                            acc[f] = vmuls(wv[j], q[f][j]);
-                        }
-                        ++po;
-                    } else {
+                for (int f = 0; f < kRows; ++f) {
+                    if (start) po[f * (kRowWords / 2)] = acc[f];
+                    acc[f] = __ffma2_rn(wv[j], make_float2(q[f][j], q[f][j]), vmuls(acc[f], keep));
+                }
+                po += start ? 1 : 0;
+            });
 #pragma unroll
-                        for (int f = 0; f < nf; ++f) acc[f] = vfmas(wv[j], q[f][j], acc[f]);
-                    }
-                });
-#pragma unroll
-                for (int f = 0; f < nf; ++f) po[f * (kRowWords / 2)] = acc[f];
-            };
-            walk(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
-            walk(std::integral_constant<int, 4>{}, std::integral_constant<int, 3>{});
+            for (int f = 0; f < kRows; ++f) po[f * (kRowWords / 2)] = acc[f];
         }
         __syncwarp();
 
         // ---------------- mel step 2: band per lane, out[m] = sum V(runs of segment m) + sum U(runs of segment m+1)
         {
             float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
-            const float2* P = reinterpret_cast<const float2*>(R);
-            for (int m = lane; m < M; m += 32) {
-                const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
-                float v[kRows];
+            if (M <= 64) {
+                // fixed slots: <= 4 runs per segment, run numbers held packed in registers (absent -> the zero run)
 #pragma unroll
-                for (int f = 0; f < kRows; ++f) v[f] = 0.0f;
-                for (int g = ga; g < gb; ++g) {
+                for (int r = 0; r < 2; ++r) {
+                    const int m = lane + 32 * r;
+                    if (m < M) {
+                        const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
+                        float v[kRows];
 #pragma unroll
-                    for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].y;
+                        for (int f = 0; f < kRows; ++f) {
+                            const float* rowp = R + f * kRowWords;
+                            const float v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
+                            const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1], v3 = rowp[2 * (pv >> 24) + 1];
+                            const float u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
+                            const float u2 = rowp[2 * ((pu >> 16) & 0xff)], u3 = rowp[2 * (pu >> 24)];
+                            v[f] = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
+                        }
+#pragma unroll
+                        for (int f = 0; f < 4; ++f)                          // 10*log10(max(v, amin))
+                            ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
+#pragma unroll
+                        for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
+                    }
                 }
-                for (int g = gb; g < gc; ++g) {
+            } else {
+                const float2* P = reinterpret_cast<const float2*>(R);
+                for (int m = lane; m < M; m += 32) {
+                    const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
+                    float v[kRows];
 #pragma unroll
-                    for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].x;
+                    for (int f = 0; f < kRows; ++f) v[f] = 0.0f;
+                    for (int g = ga; g < gb; ++g) {
+#pragma unroll
+                        for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].y;
+                    }
+                    for (int g = gb; g < gc; ++g) {
+#pragma unroll
+                        for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].x;
+                    }
+#pragma unroll
+                    for (int f = 0; f < 4; ++f)
+                        ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
+#pragma unroll
+                    for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
                 }
-#pragma unroll
-                for (int f = 0; f < 4; ++f)                                  // 10*log10(max(v, amin))
-                    ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
-#pragma unroll
-                for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
             }
         }
         __syncwarp();                                                       // rows are reused by the next frame's exchange
