@@ -68,19 +68,18 @@ __device__ __forceinline__ void mel_walk(float* R, const float2 (&wv)[17], const
     int po = g0;                                                    // float2 index of the lane's current run
 #pragma unroll
     for (int f = 0; f < NF; ++f) acc[f] = vmuls(wv[0], q[f][0]);
+    // branch-free: where a new run starts the finished pair is stored and the accumulator restarts
+    // (acc * keep, keep = 0): one FMUL2 + one FFMA2 + one predicated store per bin and row
     static_for<1, 17>([&](auto ji) {
         constexpr int j = decltype(ji)::value;
-        if ((runmask >> j) & 1u) {                                  // a new run starts at this bin
+        const bool start = (runmask >> j) & 1u;
+        const float keep = start ? 0.0f : 1.0f;
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                reinterpret_cast<float2*>(R + rows[f] * kRowWords)[po] = acc[f];
-                acc[f] = vmuls(wv[j], q[f][j]);
-            }
-            ++po;
-        } else {
-#pragma unroll
-            for (int f = 0; f < NF; ++f) acc[f] = vfmas(wv[j], q[f][j], acc[f]);
+        for (int f = 0; f < NF; ++f) {
+            if (start) reinterpret_cast<float2*>(R + rows[f] * kRowWords)[po] = acc[f];
+            acc[f] = __ffma2_rn(wv[j], make_float2(q[f][j], q[f][j]), vmuls(acc[f], keep));
         }
+        po += start ? 1 : 0;
     });
 #pragma unroll
     for (int f = 0; f < NF; ++f) reinterpret_cast<float2*>(R + rows[f] * kRowWords)[po] = acc[f];
