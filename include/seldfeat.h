@@ -49,6 +49,13 @@ int64_t seld_num_frames(const seld_plan* plan, int64_t L);
 int seld_logmel_iv_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
                        int64_t stride_b, int64_t stride_c, float* out, void* stream);
 
+/* Same with 16-bit PCM input: x holds the int16 samples a wav/flac decoder yields;
+ * the kernel converts exactly as soundfile's float32 read does (s / 32768), so the result is
+ * bit-identical to seld_logmel_iv_f32 on the converted waveform while reading half the bytes.
+ * C must be 4. */
+int seld_logmel_iv_i16(const seld_plan* plan, const int16_t* x, int64_t B, int C, int64_t L,
+                       int64_t stride_b, int64_t stride_c, float* out, void* stream);
+
 /* Same computation with HOST buffers: x_host (B, C, L) contiguous and out_host (B, C+3, T, n_mels)
  * contiguous, ideally page-locked.  The batch is cut into chunks of `chunk_clips` clips (<= 0:
  * library default) that flow through three plan-owned device slots on three internal streams, so
@@ -57,6 +64,9 @@ int seld_logmel_iv_f32(const seld_plan* plan, const float* x, int64_t B, int C, 
  * returns once everything is enqueued.  Device slots are allocated on first use and kept in the
  * plan (this is the one compute entry point that may allocate, on its first call per size). */
 int seld_logmel_iv_f32_host(seld_plan* plan, const float* x_host, int64_t B, int C, int64_t L,
+                            float* out_host, int chunk_clips, void* stream);
+/* ... and with int16 PCM host input (half the host->device bytes). */
+int seld_logmel_iv_i16_host(seld_plan* plan, const int16_t* x_host, int64_t B, int C, int64_t L,
                             float* out_host, int chunk_clips, void* stream);
 
 /* Logmel_Extractor.forward (feature.py:76-91): x (B, C>=1, L) -> out (B, C, T, n_mels). */

@@ -23,7 +23,11 @@ SIGNATURES = {
     'seld_num_frames': (_i64, [ctypes.c_void_p, _i64]),
     'seld_logmel_iv_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64, _i64, _i64,
                                           ctypes.c_void_p, ctypes.c_void_p]),
+    'seld_logmel_iv_i16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64, _i64, _i64,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     'seld_logmel_iv_f32_host': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64,
+                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    'seld_logmel_iv_i16_host': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64,
                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     'seld_logmel_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64, _i64, _i64,
                                        ctypes.c_void_p, ctypes.c_void_p]),

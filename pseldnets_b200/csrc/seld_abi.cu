@@ -232,8 +232,8 @@ extern "C" int64_t seld_num_frames(const seld_plan* p, int64_t L) {
     return 1 + L / p->dev.hop;
 }
 
-static int run_foa(const seld_plan* p, bool iv, const float* x, int64_t B, int C, int64_t L,
-                   int64_t stride_b, int64_t stride_c, float* out, void* stream) {
+static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C, int64_t L,
+                   int64_t stride_b, int64_t stride_c, float* out, void* stream, bool i16 = false) {
     if (!p || B < 0 || C < 1 || L < 1) return SELD_EINVAL;
     if (iv && C < 4) return SELD_EINVAL;               // intensityvector indexes channels 0..3
     if (L <= p->n_fft / 2) return SELD_ESHORT;         // reflect padding needs pad < L (torch.stft)
@@ -244,7 +244,8 @@ static int run_foa(const seld_plan* p, bool iv, const float* x, int64_t B, int C
     seld::FoaArgs a;
     a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
     a.B = (int)B; a.C = C; a.Cout = C + (iv ? 3 : 0); a.T = (int)T; a.c_lo = 0;
-    a.span = 0; a.vec_ok = 0;
+    a.span = 0; a.vec_ok = 0; a.in_i16 = i16 ? 1 : 0; a.in_scale = i16 ? 1.0f / 32768.0f : 1.0f;
+    if (i16 && !(iv && p->iv_kernel == 2 && C == 4)) return SELD_EUNSUPPORTED;   // PCM input: 4-channel iv2 path only
     cudaStream_t st = (cudaStream_t)stream;
     bool general_iv = iv;
     if (iv && p->use_iv2) {
@@ -277,9 +278,17 @@ extern "C" int seld_logmel_iv_f32(const seld_plan* p, const float* x, int64_t B,
     return run_foa(p, true, x, B, C, L, stride_b, stride_c, out, stream);
 }
 
-extern "C" int seld_logmel_iv_f32_host(seld_plan* p, const float* x_host, int64_t B, int C, int64_t L,
-                                       float* out_host, int chunk_clips, void* stream) {
+extern "C" int seld_logmel_iv_i16(const seld_plan* p, const int16_t* x, int64_t B, int C, int64_t L,
+                                  int64_t stride_b, int64_t stride_c, float* out, void* stream) {
+    return run_foa(p, true, x, B, C, L, stride_b, stride_c, out, stream, true);
+}
+
+static int iv_host_pipeline(seld_plan* p, const void* x_host_v, bool i16, int64_t B, int C, int64_t L,
+                            float* out_host, int chunk_clips, void* stream) {
+    const unsigned char* x_host = (const unsigned char*)x_host_v;
+    const size_t esz = i16 ? 2 : 4;
     if (!p || B < 0 || C < 4 || L < 1) return SELD_EINVAL;
+    if (i16 && C != 4) return SELD_EUNSUPPORTED;
     if (L <= p->n_fft / 2) return SELD_ESHORT;
     if (B == 0) return SELD_OK;
     if (!x_host || !out_host) return SELD_EINVAL;
@@ -305,7 +314,7 @@ extern "C" int seld_logmel_iv_f32_host(seld_plan* p, const float* x_host, int64_
         }
         hp.ready = true;
     }
-    const size_t need_in = (size_t)(cc * in_clip) * 4, need_out = (size_t)(cc * out_clip) * 4;
+    const size_t need_in = (size_t)(cc * in_clip) * esz, need_out = (size_t)(cc * out_clip) * 4;
     if (need_in > hp.cap_in || need_out > hp.cap_out) {
         SELD_TRY(cudaStreamSynchronize(hp.s_in)); SELD_TRY(cudaStreamSynchronize(hp.s_k)); SELD_TRY(cudaStreamSynchronize(hp.s_out));
         pipe_free_slots(hp);
@@ -328,10 +337,10 @@ extern "C" int seld_logmel_iv_f32_host(seld_plan* p, const float* x_host, int64_
             SELD_TRY(cudaStreamWaitEvent(hp.s_in, hp.ev_k[sl], 0));
             SELD_TRY(cudaStreamWaitEvent(hp.s_k, hp.ev_out[sl], 0));
         }
-        SELD_TRY(cudaMemcpyAsync(hp.din[sl], x_host + b0 * in_clip, (size_t)(nb * in_clip) * 4, cudaMemcpyHostToDevice, hp.s_in));
+        SELD_TRY(cudaMemcpyAsync(hp.din[sl], x_host + (size_t)(b0 * in_clip) * esz, (size_t)(nb * in_clip) * esz, cudaMemcpyHostToDevice, hp.s_in));
         SELD_TRY(cudaEventRecord(hp.ev_in[sl], hp.s_in));
         SELD_TRY(cudaStreamWaitEvent(hp.s_k, hp.ev_in[sl], 0));
-        const int rc = run_foa(p, true, hp.din[sl], nb, C, L, in_clip, L, hp.dout[sl], hp.s_k);
+        const int rc = run_foa(p, true, hp.din[sl], nb, C, L, in_clip, L, hp.dout[sl], hp.s_k, i16);
         if (rc != SELD_OK) { cudaSetDevice(prev); return rc; }
         SELD_TRY(cudaEventRecord(hp.ev_k[sl], hp.s_k));
         SELD_TRY(cudaStreamWaitEvent(hp.s_out, hp.ev_k[sl], 0));
@@ -343,6 +352,16 @@ extern "C" int seld_logmel_iv_f32_host(seld_plan* p, const float* x_host, int64_
 #undef SELD_TRY
     cudaSetDevice(prev);
     return SELD_OK;
+}
+
+extern "C" int seld_logmel_iv_f32_host(seld_plan* p, const float* x_host, int64_t B, int C, int64_t L,
+                                       float* out_host, int chunk_clips, void* stream) {
+    return iv_host_pipeline(p, x_host, false, B, C, L, out_host, chunk_clips, stream);
+}
+
+extern "C" int seld_logmel_iv_i16_host(seld_plan* p, const int16_t* x_host, int64_t B, int C, int64_t L,
+                                       float* out_host, int chunk_clips, void* stream) {
+    return iv_host_pipeline(p, x_host, true, B, C, L, out_host, chunk_clips, stream);
 }
 
 extern "C" int seld_logmel_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,
@@ -377,7 +396,7 @@ extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B
     seld::FoaArgs a;
     a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
     a.B = (int)B; a.C = C; a.Cout = C + C * (C - 1) / 2; a.T = (int)T; a.c_lo = 0;
-    a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.span = 0; a.vec_ok = 0;
+    a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.span = 0; a.vec_ok = 0; a.in_i16 = 0; a.in_scale = 1.0f;
     const bool use_top_db = top_db >= 0.0f;
     cudaError_t e = seld::mic_launch(a, p->dev, (int*)workspace, top_db, use_top_db, p->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);

@@ -206,7 +206,7 @@ foa_features_kernel(const FoaArgs a, const PlanDev pd) {
         const int nf = min(kWarps, a.T - t0);
         const int64_t s0 = (int64_t)t0 * hop - 512;                         // first staged sample
         const int valid = (nf - 1) * hop + 1024;                            // samples actually needed
-        const float* xb = a.x + (int64_t)b * a.stride_b + (int64_t)c_base * a.stride_c;
+        const float* xb = static_cast<const float*>(a.x) + (int64_t)b * a.stride_b + (int64_t)c_base * a.stride_c;
 
         __syncthreads();                                                    // previous tile's readers done
         if (a.vec_ok && s0 >= 0 && s0 + span <= a.L) {                      // interior: 16-byte loads

@@ -34,8 +34,10 @@ constexpr int kWabStride = 36;            // floats per lane in the (a, b) weigh
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-template <int W>
-__global__ void __launch_bounds__(W * 32, 1) 
+// TIn = float (the reference's input) or int16_t (PCM as decoded from wav/flac: soundfile's float32
+// conversion is s / 32768, folded exactly into the window: a.in_scale = 2^-15)
+template <int W, typename TIn>
+__global__ void __launch_bounds__(W * 32, 1)
 foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);                    // 1024 float2
@@ -55,7 +57,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     const uint32_t runmask = pd.runmask[lane];
     const int g0 = pd.g0[lane];
     const int hop = pd.hop, M = pd.n_mels;
-    const float eps = pd.eps, amin = pd.amin;
+    const float eps = pd.eps, amin = pd.amin, in_scale = a.in_scale;
     // writer: bin k = lane + 32*kb lands at word 32*kb + wofs[kb & 3] of its row
     int wofs[4];
 #pragma unroll
@@ -81,20 +83,20 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         const int b = tile / a.tiles_per_clip;
         const int t = (tile - b * a.tiles_per_clip) * W + warp;
         if (t >= a.T) continue;
-        const float* xb = a.x + (int64_t)b * a.stride_b;
+        const TIn* xb = reinterpret_cast<const TIn*>(a.x) + (int64_t)b * a.stride_b;
         const int64_t s0 = (int64_t)t * hop - 512;
 
         float2 re[32], im[32];
         // ---------------- load + window: re = (ch0, ch2), im = (ch1, ch3)
         if (s0 >= 0 && s0 + 1024 <= a.L) {
-            const float* p0 = xb + s0 + lane;
-            const float* p1 = p0 + a.stride_c;
-            const float* p2 = p1 + a.stride_c;
-            const float* p3 = p2 + a.stride_c;
+            const TIn* p0 = xb + s0 + lane;
+            const TIn* p1 = p0 + a.stride_c;
+            const TIn* p2 = p1 + a.stride_c;
+            const TIn* p3 = p2 + a.stride_c;
             static_for<0, 32>([&](auto mi) {
                 constexpr int m = decltype(mi)::value;
-                re[m] = make_float2(__ldg(p0 + 32 * m), __ldg(p2 + 32 * m));
-                im[m] = make_float2(__ldg(p1 + 32 * m), __ldg(p3 + 32 * m));
+                re[m] = make_float2((float)__ldg(p0 + 32 * m), (float)__ldg(p2 + 32 * m));
+                im[m] = make_float2((float)__ldg(p1 + 32 * m), (float)__ldg(p3 + 32 * m));
             });
         } else {                                                            // reflect padding at the clip edges
             static_for<0, 32>([&](auto mi) {
@@ -102,14 +104,14 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 int64_t s = s0 + 32 * m + lane;
                 if (s < 0) s = -s;
                 if (s >= a.L) s = 2 * (a.L - 1) - s;
-                const float* p = xb + s;
-                re[m] = make_float2(__ldg(p), __ldg(p + 2 * a.stride_c));
-                im[m] = make_float2(__ldg(p + a.stride_c), __ldg(p + 3 * a.stride_c));
+                const TIn* p = xb + s;
+                re[m] = make_float2((float)__ldg(p), (float)__ldg(p + 2 * a.stride_c));
+                im[m] = make_float2((float)__ldg(p + a.stride_c), (float)__ldg(p + 3 * a.stride_c));
             });
         }
         static_for<0, 32>([&](auto mi) {
             constexpr int m = decltype(mi)::value;
-            const float w = win_s[32 * m + lane];
+            const float w = win_s[32 * m + lane] * in_scale;
             re[m] = vmuls(re[m], w);
             im[m] = vmuls(im[m], w);
         });
@@ -299,20 +301,21 @@ bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin) {
 
 int foa_iv2_frames_per_tile() { return iv2_warps(); }
 
-template <int W>
+template <int W, typename TIn>
 static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
     const size_t smem = iv2_smem_bytes<W>(pd);
-    cudaError_t e = cudaFuncSetAttribute(foa_iv2_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
-    foa_iv2_kernel<W><<<gx, W * 32, smem, st>>>(a, pd);
+    foa_iv2_kernel<W, TIn><<<gx, W * 32, smem, st>>>(a, pd);
     return cudaGetLastError();
 }
 
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
+    if (a.in_i16) return iv2_launch_t<8, int16_t>(a, pd, sm_count, st);
     switch (iv2_warps()) {
-        case 12: return iv2_launch_t<12>(a, pd, sm_count, st);
-        default: return iv2_launch_t<8>(a, pd, sm_count, st);
+        case 12: return iv2_launch_t<12, float>(a, pd, sm_count, st);
+        default: return iv2_launch_t<8, float>(a, pd, sm_count, st);
     }
 }
 

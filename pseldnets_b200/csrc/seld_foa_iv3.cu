@@ -81,7 +81,7 @@ foa_iv3_kernel(const FoaArgs a, const PlanDev pd) {
         const int b = tile / a.tiles_per_clip;
         const int t = (tile - b * a.tiles_per_clip) * NP + pair;
         if (t >= a.T) continue;                                            // both warps of the pair skip together
-        const float* xa = a.x + (int64_t)b * a.stride_b + (int64_t)(2 * role) * a.stride_c;
+        const float* xa = static_cast<const float*>(a.x) + (int64_t)b * a.stride_b + (int64_t)(2 * role) * a.stride_c;
         const int64_t s0 = (int64_t)t * hop - 512;
 
         float2 pr[16], pi[16];
@@ -113,7 +113,7 @@ foa_iv3_kernel(const FoaArgs a, const PlanDev pd) {
                 const int tn = (tile_n - bn * a.tiles_per_clip) * NP + pair;
                 const int64_t sn = (int64_t)tn * hop - 512 + 32 * lane;
                 if (tn < a.T && sn >= 0 && sn + 32 <= a.L) {
-                    const float* pn = a.x + (int64_t)bn * a.stride_b + (int64_t)(2 * role) * a.stride_c + sn;
+                    const float* pn = static_cast<const float*>(a.x) + (int64_t)bn * a.stride_b + (int64_t)(2 * role) * a.stride_c + sn;
                     prefetch_l2(pn);
                     prefetch_l2(pn + a.stride_c);
                 }

@@ -97,7 +97,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         const int t = (tile - b * a.tiles_per_clip) * W + warp;
         if (t >= a.T) continue;
         if (b != cur_b) { flush_max(); cur_b = b; }
-        const float* xb = a.x + (int64_t)b * a.stride_b;
+        const float* xb = static_cast<const float*>(a.x) + (int64_t)b * a.stride_b;
         const int64_t s0 = (int64_t)t * hop - 512;
 
         float2 re[32], im[32];

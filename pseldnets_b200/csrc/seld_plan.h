@@ -31,7 +31,9 @@ struct PlanDev {
 };
 
 struct FoaArgs {
-    const float* x;          // (B, C, L) fp32, strides in elements
+    const void* x;           // (B, C, L) fp32 (or int16 PCM when in_i16), strides in elements
+    float in_scale;          // 1 for fp32 input, 2^-15 for int16 PCM
+    int in_i16;
     int64_t stride_b, stride_c;
     float* out;              // (B, Cout, T, M) contiguous
     int64_t L;

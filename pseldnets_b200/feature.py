@@ -58,6 +58,7 @@ class _Plan:
 
 class _ExtractorBase(nn.Module):
     _entry = None       # C-ABI symbol
+    _entry_i16 = None   # C-ABI symbol for int16 PCM input, if the path has one
     _extra_ch = 0
 
     def __init__(self, cfg):
@@ -100,7 +101,10 @@ class _ExtractorBase(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('pseldnets_b200 extractors run on CUDA tensors only (no CPU path); '
                                'got a tensor on %s' % x.device)
-        if x.dtype != torch.float32:
+        entry = self._entry
+        if x.dtype == torch.int16 and self._entry_i16 is not None:
+            entry = self._entry_i16          # 16-bit PCM as decoded from wav/flac: converted in-kernel as s / 32768
+        elif x.dtype != torch.float32:
             raise TypeError('expected float32 waveform, got %s' % x.dtype)
         if x.stride(2) != 1:
             x = x.contiguous()
@@ -112,9 +116,9 @@ class _ExtractorBase(nn.Module):
         T = 1 + L // self.hop
         out = torch.empty((B, C + self._extra_ch, T, self.n_mels), dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        fn = getattr(_abi.lib(), self._entry)
+        fn = getattr(_abi.lib(), entry)
         code = fn(plan.handle, x.data_ptr(), B, C, L, x.stride(0), x.stride(1), out.data_ptr(), stream)
-        _abi.check(code, self._entry)
+        _abi.check(code, entry)
         return out
 
 
@@ -122,6 +126,7 @@ class LogmelIV_Extractor(_ExtractorBase):
     """log-mel of every channel + mel-projected normalised intensity vector of channels 1..3
     against channel 0 (FOA: W, Y, Z, X).  feature.py:20-56, 93-117."""
     _entry = 'seld_logmel_iv_f32'
+    _entry_i16 = 'seld_logmel_iv_i16'
     _extra_ch = 3
 
 
@@ -134,8 +139,8 @@ class LogmelIV_Extractor(_ExtractorBase):
         if x.ndim != 3:
             raise ValueError("x shape must be (batch_size, num_channels, data_length)\n \
                             Now it is {}".format(x.shape))
-        if x.is_cuda or x.dtype != torch.float32:
-            raise TypeError('forward_host expects a CPU float32 tensor')
+        if x.is_cuda or x.dtype not in (torch.float32, torch.int16):
+            raise TypeError('forward_host expects a CPU float32 (or int16 PCM) tensor')
         x = x.contiguous()
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if dev.index is None:
@@ -146,9 +151,9 @@ class LogmelIV_Extractor(_ExtractorBase):
             out = torch.empty((B, C + 3, T, self.n_mels), dtype=torch.float32, pin_memory=True)
         plan = self._plan(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        code = _abi.lib().seld_logmel_iv_f32_host(plan.handle, x.data_ptr(), B, C, L, out.data_ptr(),
-                                                  int(chunk_clips), stream)
-        _abi.check(code, 'seld_logmel_iv_f32_host')
+        name = 'seld_logmel_iv_i16_host' if x.dtype == torch.int16 else 'seld_logmel_iv_f32_host'
+        code = getattr(_abi.lib(), name)(plan.handle, x.data_ptr(), B, C, L, out.data_ptr(), int(chunk_clips), stream)
+        _abi.check(code, name)
         return out
 
 

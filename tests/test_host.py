@@ -115,3 +115,25 @@ def test_host_model_of_warp_fft(tmp_path):
     Ar, Br = np.fft.rfft(2 * a.astype(np.float64)), np.fft.rfft(2 * b.astype(np.float64))
     assert np.abs((A[0::2] + 1j * A[1::2]) - Ar).max() < 1e-6 * np.abs(Ar).max()
     assert np.abs((Bv[0::2] + 1j * Bv[1::2]) - Br).max() < 1e-6 * np.abs(Br).max()
+
+
+def test_segment_index_matches_reference_cases():
+    """inference.segment_index restates src/utils/data_utilities.py:6-64: short clip, exact fit,
+    long remainder (zero-padded last chunk), short remainder (last chunk shifted back)."""
+    from pseldnets_b200 import inference as inf
+    assert inf.segment_index(5, 10, 5) == ([(0, 5)], [(0, 5)])
+    assert inf.segment_index(20, 10, 5) == ([(0, 10), (5, 15), (10, 20)], [(0, 0)] * 3)
+    assert inf.segment_index(22, 10, 5) == ([(0, 10), (5, 15), (10, 20), (15, 22)], [(0, 0)] * 3 + [(0, 3)])
+    assert inf.segment_index(23, 10, 10) == ([(0, 10), (10, 20), (13, 23)], [(0, 0)] * 3)
+    assert inf.segment_index(26, 10, 10) == ([(0, 10), (10, 20), (20, 26)], [(0, 0)] * 2 + [(0, 4)])
+    assert inf.segment_index(23, 10, 10, True)[0][-1] == (20, 23)
+    try:                                   # same answers as the reference itself where it is mounted
+        import sys
+        sys.path.insert(0, '/root/reference/src')
+        import numpy as np
+        from utils.data_utilities import segment_index as ref_si
+    except Exception:
+        return
+    for x_len, ch, hp in ((5, 10, 5), (20, 10, 5), (22, 10, 5), (23, 10, 10), (26, 10, 10), (415200, 240000, 12000)):
+        for flag in (False, True):
+            assert tuple(map(list, ref_si(np.zeros((1, x_len)), ch, hp, flag))) == tuple(map(list, inf.segment_index(x_len, ch, hp, flag)))

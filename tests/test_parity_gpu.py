@@ -248,3 +248,22 @@ def test_cfg5_epoch_sweep_scaled():
         assert torch.equal(torch.cat(parts), full), sweep                  # features: bit-identical
         got = torch.cat([shard.clip_checksums(p) for p in parts])
         assert torch.allclose(got, ref, rtol=1e-12, atol=0), sweep         # fp64 reductions: order may differ
+
+
+def test_int16_pcm_input_is_bit_identical_to_float_path():
+    """int16 PCM in (as a wav/flac decoder yields) == float32 path on s / 32768."""
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    g = torch.Generator().manual_seed(9)
+    pcm = torch.randint(-32768, 32768, (5, 4, 24000), generator=g, dtype=torch.int32).to(torch.int16)
+    pcm[1, :, 12000:] = 0                                           # padded tail
+    xf = pcm.float() / 32768.0                                      # soundfile float32 read
+    ref = ext(xf.cuda())
+    y = ext(pcm.cuda())
+    assert y.dtype == torch.float32 and torch.equal(y, ref)
+    yh = ext.forward_host(pcm.pin_memory(), chunk_clips=2)
+    torch.cuda.synchronize()
+    assert torch.equal(yh, ref.cpu())
+    with pytest.raises(_abi.SeldError):                             # PCM path covers the 4-channel FOA case only
+        ext(torch.zeros(1, 8, 2400, dtype=torch.int16, device='cuda'))
+    with pytest.raises(TypeError):
+        ext(torch.zeros(1, 4, 2400, dtype=torch.float64, device='cuda'))
