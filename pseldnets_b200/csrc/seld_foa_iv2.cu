@@ -25,10 +25,21 @@
 
 namespace seld {
 
+#ifdef SELD_PHASE_TIMING
+// Developer build: per-warp clock64 time of each phase, summed over the warp's frames.
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(i) do { const long long _t = clock64(); if (lane == 0) phase_acc[i] += _t - phase_t0; phase_t0 = _t; } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 constexpr int kRowWords = 528;            // 33 chunks of 16 bins (bin 512 opens chunk 32)
 constexpr int kRows = 7;                  // P0 P1 P2 P3 n1 n2 n3
 constexpr int kRegion = kRows * kRowWords;   // floats per warp; the 32x33 float2 exchange buffer (2112) aliases it
 constexpr int kZeroRun = 127;             // float2 slot of every row kept at (0, 0) during the combine step
+constexpr int kTwStride = 68;             // 32 float2 + pad
+constexpr int kWinStride = 36;            // 32 floats + pad
+constexpr int kXStride = 34;              // exchange buffer row stride in float2 (even: 128-bit reads)
 constexpr int kWabStride = 36;            // floats per lane in the (a, b) weight table: 17 float2 + pad, 36*l mod 32 = 4l
 
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -40,14 +51,20 @@ template <int W, typename TIn>
 __global__ void __launch_bounds__(W * 32, 1)
 foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw_s = reinterpret_cast<float2*>(smem_raw);                    // 1024 float2
-    float* win_s = reinterpret_cast<float*>(tw_s + 1024);                  // 1024
-    float* wab_s = win_s + 1024;                                           // 32 * kWabStride
+    // lane-major tables read with 128-bit loads: row stride = 4 (mod 32) words -> conflict-free
+    float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: (cos, -sin) of W1024^(lane*brev5(p)), p = 0..31
+    float* win_s = tw_s + 32 * kTwStride;                                  // [lane][kWinStride]: window[32*m + lane] * 0.5, m = 0..31
+    float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride
     int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
     float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 1024; i += W * 32) { tw_s[i] = pd.tw[i]; win_s[i] = pd.win[i]; }
+    for (int i = tid; i < 1024; i += W * 32) {
+        const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
+        const float2 w = pd.tw[brev5(r) * 32 + l];
+        tw_s[l * kTwStride + 2 * r] = w.x; tw_s[l * kTwStride + 2 * r + 1] = w.y;
+        win_s[l * kWinStride + r] = pd.win[i];
+    }
     for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
     for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
     __syncthreads();
@@ -79,10 +96,15 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     if (lane < M) { slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]); slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]); }
     if (lane + 32 < M) { slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]); slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]); }
 
+#ifdef SELD_PHASE_TIMING
+    long long phase_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long phase_t0 = clock64();
+#endif
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_clip;
         const int t = (tile - b * a.tiles_per_clip) * W + warp;
         if (t >= a.T) continue;
+        PHASE_MARK(0);
         const TIn* xb = reinterpret_cast<const TIn*>(a.x) + (int64_t)b * a.stride_b;
         const int64_t s0 = (int64_t)t * hop - 512;
 
@@ -109,32 +131,53 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 im[m] = make_float2((float)__ldg(p + a.stride_c), (float)__ldg(p + 3 * a.stride_c));
             });
         }
-        static_for<0, 32>([&](auto mi) {
-            constexpr int m = decltype(mi)::value;
-            const float w = win_s[32 * m + lane] * in_scale;
-            re[m] = vmuls(re[m], w);
-            im[m] = vmuls(im[m], w);
+        PHASE_MARK(1);   // loads issued
+        static_for<0, 8>([&](auto mi) {
+            constexpr int m4 = decltype(mi)::value;
+            const float4 w4 = *reinterpret_cast<const float4*>(win_s + lane * kWinStride + 4 * m4);
+            const float w[4] = {w4.x * in_scale, w4.y * in_scale, w4.z * in_scale, w4.w * in_scale};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                re[4 * m4 + e] = vmuls(re[4 * m4 + e], w[e]);
+                im[4 * m4 + e] = vmuls(im[4 * m4 + e], w[e]);
+            }
         });
 
+        PHASE_MARK(2);   // loads landed + window
         // ---------------- two 1024-point FFTs at once: 32-pt, twiddle, exchange, 32-pt
         fft32(re, im);
-        static_for<1, 32>([&](auto pi) {
-            constexpr int p = decltype(pi)::value;
-            constexpr int ka = brev5(p);
-            const float2 w = tw_s[ka * 32 + lane];                          // (cos, -sin)
-            const float2 r = re[p], i = im[p];
-            re[p] = vfmas(i, -w.y, vmuls(r, w.x));
-            im[p] = vfmas(i, w.x, vmuls(r, w.y));
+        PHASE_MARK(3);   // first 32-pt
+        static_for<0, 16>([&](auto pi) {
+            constexpr int p2 = decltype(pi)::value;                         // positions 2*p2, 2*p2+1
+            const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
+            if constexpr (p2 > 0) {                                         // position 0 is ka = 0: twiddle 1
+                const float2 r = re[2 * p2], i = im[2 * p2];
+                re[2 * p2] = vfmas(i, -w4.y, vmuls(r, w4.x));
+                im[2 * p2] = vfmas(i, w4.x, vmuls(r, w4.y));
+            }
+            const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
+            re[2 * p2 + 1] = vfmas(i, -w4.w, vmuls(r, w4.z));
+            im[2 * p2 + 1] = vfmas(i, w4.z, vmuls(r, w4.w));
         });
-        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = re[p]; });
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = re[p]; });
         __syncwarp();
-        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; re[j] = scratch[lane * 33 + j]; });
+        static_for<0, 16>([&](auto ji) {
+            constexpr int j = decltype(ji)::value;
+            const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
+            re[2 * j] = make_float2(v.x, v.y); re[2 * j + 1] = make_float2(v.z, v.w);
+        });
         __syncwarp();
-        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = im[p]; });
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = im[p]; });
         __syncwarp();
-        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; im[j] = scratch[lane * 33 + j]; });
+        static_for<0, 16>([&](auto ji) {
+            constexpr int j = decltype(ji)::value;
+            const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
+            im[2 * j] = make_float2(v.x, v.y); im[2 * j + 1] = make_float2(v.z, v.w);
+        });
         __syncwarp();
+        PHASE_MARK(4);   // twiddle + exchange
         fft32(re, im);                                                      // position p: Z[lane + 32*brev5(p)]
+        PHASE_MARK(5);   // second 32-pt
 
         // ---------------- per-bin quantities -> 7 rows
         {
@@ -178,6 +221,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         }
         __syncwarp();
 
+        PHASE_MARK(6);   // pointwise
         // ---------------- mel step 1: chunk walk of all seven rows, per-run partial sums (U, V) left in the rows
         {
             float2 wv[17];
@@ -224,6 +268,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         }
         __syncwarp();
 
+        PHASE_MARK(7);   // mel walk
         // ---------------- mel step 2: band per lane, out[m] = sum V(runs of segment m) + sum U(runs of segment m+1)
         {
             float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
@@ -275,13 +320,17 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             }
         }
         __syncwarp();                                                       // rows are reused by the next frame's exchange
+        PHASE_MARK(8);   // mel combine + store
     }
+#ifdef SELD_PHASE_TIMING
+    if (lane == 0) for (int i = 0; i < 10; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)phase_acc[i]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
 template <int W>
 static size_t iv2_smem_bytes(const PlanDev& pd) {
-    return (size_t)(2 * 1024 + 1024 + 32 * kWabStride + pd.gseg_pad + W * kRegion) * sizeof(float);
+    return (size_t)(32 * kTwStride + 32 * kWinStride + 32 * kWabStride + pd.gseg_pad + W * kRegion) * sizeof(float);
 }
 
 // Warps (= frames) per block.  One block per SM; more warps hide latency, fewer leave more
@@ -310,6 +359,14 @@ static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_coun
     foa_iv2_kernel<W, TIn><<<gx, W * 32, smem, st>>>(a, pd);
     return cudaGetLastError();
 }
+
+#ifdef SELD_PHASE_TIMING
+extern "C" void seld_dev_phase_cycles(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_phase_cycles, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+}
+#endif
 
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
     if (a.in_i16) return iv2_launch_t<8, int16_t>(a, pd, sm_count, st);
