@@ -267,3 +267,20 @@ def test_int16_pcm_input_is_bit_identical_to_float_path():
         ext(torch.zeros(1, 8, 2400, dtype=torch.int16, device='cuda'))
     with pytest.raises(TypeError):
         ext(torch.zeros(1, 4, 2400, dtype=torch.float64, device='cuda'))
+
+
+def test_other_configurations_against_oracle():
+    """Beyond the reference's two configs: other hops / sample rates / mel counts stay on the fast
+    kernels (n_mels > 64 uses the looped combine step) or fall back to the general one."""
+    from oracle import seld_oracle as so, synth
+    for sr, hop, n_mels, L in ((16000, 160, 64, 8000), (48000, 480, 64, 12000), (24000, 256, 64, 6000),
+                               (24000, 240, 128, 4800), (24000, 100, 40, 3000), (44100, 441, 96, 9000)):
+        cfg = make_cfg(sr, hop, 'hann', 'logmelIV', n_mels=n_mels)
+        ext = pb.LogmelIV_Extractor(cfg).cuda()
+        x = synth.white(700 + hop, 2, 4, L)
+        y = _run(ext, x)
+        ref = so.logmel_iv(x, ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy(), 1024, hop, np.float64)
+        assert y.shape == (2, 7, 1 + L // hop, n_mels)
+        assert_blocks_close(y, ref, 4, what='sr=%d hop=%d M=%d' % (sr, hop, n_mels))
+    with pytest.raises(_abi.SeldError):                  # n_fft other than 1024 is outside the kernels
+        pb.LogmelIV_Extractor(make_cfg(24000, 240, nfft=512)).cuda()(torch.zeros(1, 4, 2400, device='cuda'))
