@@ -2,7 +2,7 @@
 """Developer tool: build libseldfeat_timing.so with -DSELD_PHASE_TIMING and print where a warp of the
 iv2 kernel spends its cycles (clock64 per phase, averaged per frame).  Run on the GPU box."""
 import ctypes, os, subprocess, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pseldnets_b200 import build as b
 lib_path = os.path.join(ROOT, 'gpurun_out', 'libseldfeat_timing.so')
