@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libseldfeat.so')
+LIB_PATH = os.environ.get('SELD_LIB', os.path.join(_HERE, 'libseldfeat.so'))   # SELD_LIB: developer A/B builds
 
 SELD_OK = 0
 SELD_EINVAL, SELD_EUNSUPPORTED, SELD_ESHORT, SELD_ECUDA, SELD_ENOMEM = -1, -2, -3, -4, -5

@@ -92,9 +92,13 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         for (int i = 0; i < 4; ++i) p |= (uint32_t)(lo + i < hi ? lo + i : kZeroRun) << (8 * i);
         return p;
     };
-    uint32_t slotV0 = 0, slotU0 = 0, slotV1 = 0, slotU1 = 0;
+    constexpr uint32_t kNoRuns = kZeroRun * 0x01010101u;
+    uint32_t slotV0 = kNoRuns, slotU0 = kNoRuns, slotV1 = kNoRuns, slotU1 = kNoRuns;
     if (lane < M) { slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]); slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]); }
     if (lane + 32 < M) { slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]); slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]); }
+    // fourth slot in use by any band?  (warp-uniform; most banks never split a segment over four chunks)
+    const bool four = __any_sync(0xffffffffu, (slotV0 >> 24) != kZeroRun || (slotU0 >> 24) != kZeroRun ||
+                                              (slotV1 >> 24) != kZeroRun || (slotU1 >> 24) != kZeroRun);
 
 #ifdef SELD_PHASE_TIMING
     long long phase_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -273,29 +277,39 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         {
             float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
             if (M <= 64) {
-                // fixed slots: <= 4 runs per segment, run numbers held packed in registers (absent -> the zero run)
+                // fixed slots: <= 4 runs per segment, run numbers held packed in registers (absent -> the zero run);
+                // all loads are issued up front (a data-dependent slot count was measured 2.4 % slower)
+                auto combine = [&](auto four_c) {
+                    constexpr bool kFour = decltype(four_c)::value;
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int m = lane + 32 * r;
-                    if (m < M) {
-                        const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
-                        float v[kRows];
+                    for (int r = 0; r < 2; ++r) {
+                        const int m = lane + 32 * r;
+                        if (m < M) {
+                            const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
+                            float v[kRows];
 #pragma unroll
-                        for (int f = 0; f < kRows; ++f) {
-                            const float* rowp = R + f * kRowWords;
-                            const float v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
-                            const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1], v3 = rowp[2 * (pv >> 24) + 1];
-                            const float u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
-                            const float u2 = rowp[2 * ((pu >> 16) & 0xff)], u3 = rowp[2 * (pu >> 24)];
-                            v[f] = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
+                            for (int f = 0; f < kRows; ++f) {
+                                const float* rowp = R + f * kRowWords;
+                                const float v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
+                                const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
+                                const float u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
+                                const float u2 = rowp[2 * ((pu >> 16) & 0xff)];
+                                if constexpr (kFour) {
+                                    const float v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
+                                    v[f] = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
+                                } else {
+                                    v[f] = ((v0 + v1) + v2) + ((u0 + u1) + u2);
+                                }
+                            }
+#pragma unroll
+                            for (int f = 0; f < 4; ++f)                          // 10*log10(max(v, amin))
+                                ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
+#pragma unroll
+                            for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
                         }
-#pragma unroll
-                        for (int f = 0; f < 4; ++f)                          // 10*log10(max(v, amin))
-                            ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
-#pragma unroll
-                        for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
                     }
-                }
+                };
+                if (four) combine(std::true_type{}); else combine(std::false_type{});
             } else {
                 const float2* P = reinterpret_cast<const float2*>(R);
                 for (int m = lane; m < M; m += 32) {
