@@ -31,7 +31,11 @@ using namespace melseg;
 constexpr int kW = 8;                      // warps (frames) per block
 constexpr int kSpecStride = 516;           // float2 per channel spectrum (513 + pad)
 constexpr int kSpec = 4 * kSpecStride * 2; // floats: four spectra
-constexpr int kRowsArea = 4 * kRowWords;   // floats: 4 power rows == 32x33 float2 exchange buffer
+constexpr int kXStride = 34;                // exchange buffer row stride in float2 (even: 128-bit reads)
+constexpr int kRowsArea = 32 * kXStride * 2; // floats: 32x34 float2 exchange buffer; the 4 power rows (2112) alias it
+constexpr int kTwStride = 68;               // lane-major twiddle table row: 32 float2 + pad
+constexpr int kWinStride = 36;              // lane-major window table row: 32 floats + pad
+constexpr int kZeroRun = 127;               // float2 slot of every row kept at (0, 0) during the combine step
 constexpr int kRegion = kSpec + kRowsArea;
 
 // order-preserving float <-> int key for atomicMax
@@ -54,14 +58,20 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     using namespace mic;
     constexpr int W = kW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw_s = reinterpret_cast<float2*>(smem_raw);                    // 1024 float2 (cos, -sin)
-    float* win_s = reinterpret_cast<float*>(tw_s + 1024);                  // 1024
-    float* wab_s = win_s + 1024;                                           // 32 * kWabStride
+    // lane-major tables read with 128-bit loads (row stride = 4 mod 32 words: conflict-free)
+    float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: (cos, -sin) of W1024^(lane*brev5(p)), p = 0..31
+    float* win_s = tw_s + 32 * kTwStride;                                  // [lane][kWinStride]: window[32*m + lane] * 0.5
+    float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride
     int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
     float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 1024; i += W * 32) { tw_s[i] = pd.tw[i]; win_s[i] = pd.win[i]; }
+    for (int i = tid; i < 1024; i += W * 32) {
+        const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
+        const float2 w = pd.tw[brev5(r) * 32 + l];
+        tw_s[l * kTwStride + 2 * r] = w.x; tw_s[l * kTwStride + 2 * r + 1] = w.y;
+        win_s[l * kWinStride + r] = pd.win[i];
+    }
     for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
     for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
     __syncthreads();
@@ -77,6 +87,17 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     lane_offsets(lane, wofs, rofs);
     const int64_t ch_stride = (int64_t)a.T * M;
     const int src = (32 - lane) & 31;
+
+    auto pack_runs = [&](int lo, int hi) {
+        uint32_t p = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p |= (uint32_t)(lo + i < hi ? lo + i : kZeroRun) << (8 * i);
+        return p;
+    };
+    const uint32_t slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]), slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]);
+    const uint32_t slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]), slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]);
+    const bool four = __any_sync(0xffffffffu, (slotV0 >> 24) != kZeroRun || (slotU0 >> 24) != kZeroRun ||
+                                              (slotV1 >> 24) != kZeroRun || (slotU1 >> 24) != kZeroRun);
 
     int cur_b = -1;
     float rmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -122,30 +143,46 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 im[m] = in ? make_float2(__ldg(p + a.stride_c), __ldg(p + 3 * a.stride_c)) : make_float2(0.f, 0.f);
             });
         }
-        static_for<0, 32>([&](auto mi) {
-            constexpr int m = decltype(mi)::value;
-            const float w = win_s[32 * m + lane];
-            re[m] = vmuls(re[m], w);
-            im[m] = vmuls(im[m], w);
+        static_for<0, 8>([&](auto mi) {
+            constexpr int m4 = decltype(mi)::value;
+            const float4 w4 = *reinterpret_cast<const float4*>(win_s + lane * kWinStride + 4 * m4);
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                re[4 * m4 + e] = vmuls(re[4 * m4 + e], w[e]);
+                im[4 * m4 + e] = vmuls(im[4 * m4 + e], w[e]);
+            }
         });
 
         // ---------------- forward: two 1024-point FFTs at once
         fft32(re, im);
-        static_for<1, 32>([&](auto pi) {
-            constexpr int p = decltype(pi)::value;
-            constexpr int ka = brev5(p);
-            const float2 w = tw_s[ka * 32 + lane];
-            const float2 r = re[p], i = im[p];
-            re[p] = vfmas(i, -w.y, vmuls(r, w.x));
-            im[p] = vfmas(i, w.x, vmuls(r, w.y));
+        static_for<0, 16>([&](auto pi) {
+            constexpr int p2 = decltype(pi)::value;                         // positions 2*p2, 2*p2+1
+            const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
+            if constexpr (p2 > 0) {
+                const float2 r = re[2 * p2], i = im[2 * p2];
+                re[2 * p2] = vfmas(i, -w4.y, vmuls(r, w4.x));
+                im[2 * p2] = vfmas(i, w4.x, vmuls(r, w4.y));
+            }
+            const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
+            re[2 * p2 + 1] = vfmas(i, -w4.w, vmuls(r, w4.z));
+            im[2 * p2 + 1] = vfmas(i, w4.z, vmuls(r, w4.w));
         });
-        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = re[p]; });
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = re[p]; });
         __syncwarp();
-        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; re[j] = scratch[lane * 33 + j]; });
+        static_for<0, 16>([&](auto ji) {
+            constexpr int j = decltype(ji)::value;
+            const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
+            re[2 * j] = make_float2(v.x, v.y); re[2 * j + 1] = make_float2(v.z, v.w);
+        });
         __syncwarp();
-        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = im[p]; });
+        static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = im[p]; });
         __syncwarp();
-        static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; im[j] = scratch[lane * 33 + j]; });
+        static_for<0, 16>([&](auto ji) {
+            constexpr int j = decltype(ji)::value;
+            const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
+            im[2 * j] = make_float2(v.x, v.y); im[2 * j + 1] = make_float2(v.z, v.w);
+        });
         __syncwarp();
         fft32(re, im);
 
@@ -192,25 +229,37 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             float2 wv[17];
             load_weights(wab_s, lane, wv);
             mel_walk<4, 0, 1, 2, 3>(R, wv, rofs, runmask, g0, lane);
+            if (lane < 4) reinterpret_cast<float2*>(R + lane * kRowWords)[kZeroRun] = make_float2(0.f, 0.f);   // bins long consumed
             __syncwarp();
-            for (int m = lane; m < M; m += 32) {
-                const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int g = ga; g < gb; ++g) {
+            // band per lane; run numbers of segment m (V) and m+1 (U) in fixed slots (absent -> the zero run), all
+            // loads issued up front (n_mels == 64 on this path: bands lane and lane + 32)
+            auto combine = [&](auto four_c) {
+                constexpr bool kFour = decltype(four_c)::value;
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) v[f] += reinterpret_cast<const float2*>(R + f * kRowWords)[g].y;
-                }
-                for (int g = gb; g < gc; ++g) {
+                for (int r = 0; r < 2; ++r) {
+                    const int m = lane + 32 * r;
+                    const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) v[f] += reinterpret_cast<const float2*>(R + f * kRowWords)[g].x;
+                    for (int f = 0; f < 4; ++f) {
+                        const float* rowp = R + f * kRowWords;
+                        const float v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
+                        const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
+                        const float u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
+                        const float u2 = rowp[2 * ((pu >> 16) & 0xff)];
+                        float v;
+                        if constexpr (kFour) {
+                            const float v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
+                            v = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
+                        } else {
+                            v = ((v0 + v1) + v2) + ((u0 + u1) + u2);
+                        }
+                        const float db = 3.01029995663981195f * __log2f(fmaxf(v, amin));
+                        rmax[f] = fmaxf(rmax[f], db);
+                        ob[f * ch_stride + m] = db;
+                    }
                 }
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const float db = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
-                    rmax[f] = fmaxf(rmax[f], db);
-                    ob[f * ch_stride + m] = db;
-                }
-            }
+            };
+            if (four) combine(std::true_type{}); else combine(std::false_type{});
             __syncwarp();                                                   // rows become the exchange buffer again
         }
 
@@ -239,21 +288,33 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             });
             // inverse 32-point stage over m: swap(FFT(swap(z)))
             fft32(im, re);                                                  // position p: A[lane][n2 = brev5(p)]
-            static_for<1, 32>([&](auto pi) {
-                constexpr int p = decltype(pi)::value;
-                constexpr int n2 = brev5(p);
-                const float2 w = tw_s[n2 * 32 + lane];                      // (cos, -sin): multiply by (cos + i sin)
-                const float2 r = re[p], i = im[p];
-                re[p] = vfmas(i, w.y, vmuls(r, w.x));
-                im[p] = vfmas(i, w.x, vmuls(r, -w.y));
+            static_for<0, 16>([&](auto pi) {                                // table holds (cos, -sin): multiply by (cos + i sin)
+                constexpr int p2 = decltype(pi)::value;
+                const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
+                if constexpr (p2 > 0) {
+                    const float2 r = re[2 * p2], i = im[2 * p2];
+                    re[2 * p2] = vfmas(i, w4.y, vmuls(r, w4.x));
+                    im[2 * p2] = vfmas(i, w4.x, vmuls(r, -w4.y));
+                }
+                const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
+                re[2 * p2 + 1] = vfmas(i, w4.w, vmuls(r, w4.z));
+                im[2 * p2 + 1] = vfmas(i, w4.z, vmuls(r, -w4.w));
             });
-            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = re[p]; });
+            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = re[p]; });
             __syncwarp();
-            static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; re[j] = scratch[lane * 33 + j]; });
+            static_for<0, 16>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
+                re[2 * j] = make_float2(v.x, v.y); re[2 * j + 1] = make_float2(v.z, v.w);
+            });
             __syncwarp();
-            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * 33 + lane] = im[p]; });
+            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = im[p]; });
             __syncwarp();
-            static_for<0, 32>([&](auto ji) { constexpr int j = decltype(ji)::value; im[j] = scratch[lane * 33 + j]; });
+            static_for<0, 16>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
+                im[2 * j] = make_float2(v.x, v.y); im[2 * j + 1] = make_float2(v.z, v.w);
+            });
             __syncwarp();
             // second stage, only n1 = 0 (lag n2 = lane) and n1 = 31 (lag lane - 32):
             //   c0 = sum_k1 A'[k1],  c31 = sum_k1 A'[k1] * (cos(2 pi k1/32) - i sin(2 pi k1/32))
@@ -301,7 +362,7 @@ __global__ void mic_topdb_kernel(float* __restrict__ out, const int* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 static size_t mic_smem_bytes(const PlanDev& pd) {
-    return (size_t)(2 * 1024 + 1024 + 32 * melseg::kWabStride + pd.gseg_pad + mic::kW * mic::kRegion) * sizeof(float);
+    return (size_t)(32 * mic::kTwStride + 32 * mic::kWinStride + 32 * melseg::kWabStride + pd.gseg_pad + mic::kW * mic::kRegion) * sizeof(float);
 }
 
 bool mic_supported(const PlanDev& pd, size_t smem_optin) {
