@@ -261,6 +261,18 @@ static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C,
         if (C == 4) return SELD_OK;
         a.c_lo = 4; general_iv = false;
     }
+    if (!general_iv && p->iv_kernel == 2 && !i16 && !getenv("SELD_NO_LM4")) {
+        // log-mel of channels [c_lo, C): the packed dual-FFT kernel in its log-mel-only mode
+        const int64_t jobs = T * (int64_t)(C - a.c_lo);
+        const int jpt = seld::foa_lm4_jobs_per_tile();
+        const int64_t tpc = (jobs + jpt - 1) / jpt;
+        if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
+        a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc);
+        cudaError_t e = seld::foa_lm4_launch(a, p->dev, p->sm_count, st);
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return SELD_OK;
+    }
     const int fpt = seld::foa_frames_per_tile();
     const int64_t tiles_per_clip = (T + fpt - 1) / fpt;
     if (B * tiles_per_clip > INT32_MAX) return SELD_EUNSUPPORTED;

@@ -34,7 +34,7 @@ __device__ unsigned long long g_phase_cycles[16];
 #endif
 
 constexpr int kRowWords = 528;            // 33 chunks of 16 bins (bin 512 opens chunk 32)
-constexpr int kRows = 7;                  // P0 P1 P2 P3 n1 n2 n3
+constexpr int kRows = 7;                  // P0 P1 P2 P3 n1 n2 n3 (log-mel only: the first 4)
 constexpr int kRegion = kRows * kRowWords;   // floats per warp; the 32x33 float2 exchange buffer (2112) aliases it
 constexpr int kZeroRun = 127;             // float2 slot of every row kept at (0, 0) during the combine step
 constexpr int kTwStride = 68;             // 32 float2 + pad
@@ -47,7 +47,11 @@ __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz
 
 // TIn = float (the reference's input) or int16_t (PCM as decoded from wav/flac: soundfile's float32
 // conversion is s / 32768, folded exactly into the window: a.in_scale = 2^-15)
-template <int W, typename TIn>
+// kIV = true : one warp = one frame of a 4-channel clip -> 4 log-mel + 3 IV rows (LogmelIV_Extractor).
+// kIV = false: log-mel only (Logmel_Extractor, or channels >= 4 of a wider IV call).  The four transform
+//              slots of a warp then take four consecutive (frame, channel) jobs, j = t * Cj + c with
+//              Cj = C - c_lo channels, so any channel count keeps all four slots busy (C = 1: four frames).
+template <int W, typename TIn, bool kIV>
 __global__ void __launch_bounds__(W * 32, 1)
 foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -106,34 +110,83 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 #endif
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_clip;
-        const int t = (tile - b * a.tiles_per_clip) * W + warp;
-        if (t >= a.T) continue;
+        const int grp = (tile - b * a.tiles_per_clip) * W + warp;           // kIV: the frame; else: group of 4 jobs
+        int tk[4] = {0, 0, 0, 0}, ck[4] = {0, 0, 0, 0};                     // log-mel only: frame / channel of each transform slot
+        bool vk[4] = {true, true, true, true};
+        if constexpr (kIV) {
+            if (grp >= a.T) continue;
+        } else {
+            const int Cj = a.C - a.c_lo;
+            const int64_t J = (int64_t)a.T * Cj;
+            if ((int64_t)4 * grp >= J) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t j = (int64_t)4 * grp + k;
+                vk[k] = j < J;
+                tk[k] = vk[k] ? (int)(j / Cj) : 0;
+                ck[k] = a.c_lo + (vk[k] ? (int)(j % Cj) : 0);
+            }
+        }
+        const int t = grp;                                                  // kIV: the frame
         PHASE_MARK(0);
         const TIn* xb = reinterpret_cast<const TIn*>(a.x) + (int64_t)b * a.stride_b;
-        const int64_t s0 = (int64_t)t * hop - 512;
 
         float2 re[32], im[32];
-        // ---------------- load + window: re = (ch0, ch2), im = (ch1, ch3)
-        if (s0 >= 0 && s0 + 1024 <= a.L) {
-            const TIn* p0 = xb + s0 + lane;
-            const TIn* p1 = p0 + a.stride_c;
-            const TIn* p2 = p1 + a.stride_c;
-            const TIn* p3 = p2 + a.stride_c;
-            static_for<0, 32>([&](auto mi) {
-                constexpr int m = decltype(mi)::value;
-                re[m] = make_float2((float)__ldg(p0 + 32 * m), (float)__ldg(p2 + 32 * m));
-                im[m] = make_float2((float)__ldg(p1 + 32 * m), (float)__ldg(p3 + 32 * m));
-            });
-        } else {                                                            // reflect padding at the clip edges
-            static_for<0, 32>([&](auto mi) {
-                constexpr int m = decltype(mi)::value;
-                int64_t s = s0 + 32 * m + lane;
-                if (s < 0) s = -s;
-                if (s >= a.L) s = 2 * (a.L - 1) - s;
-                const TIn* p = xb + s;
-                re[m] = make_float2((float)__ldg(p), (float)__ldg(p + 2 * a.stride_c));
-                im[m] = make_float2((float)__ldg(p + a.stride_c), (float)__ldg(p + 3 * a.stride_c));
-            });
+        // ---------------- load + window: re = (slot 0, slot 2), im = (slot 1, slot 3)
+        if constexpr (kIV) {                                                // slots = channels 0-3 of frame t
+            const int64_t s0 = (int64_t)t * hop - 512;
+            if (s0 >= 0 && s0 + 1024 <= a.L) {
+                const TIn* p0 = xb + s0 + lane;
+                const TIn* p1 = p0 + a.stride_c;
+                const TIn* p2 = p1 + a.stride_c;
+                const TIn* p3 = p2 + a.stride_c;
+                static_for<0, 32>([&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    re[m] = make_float2((float)__ldg(p0 + 32 * m), (float)__ldg(p2 + 32 * m));
+                    im[m] = make_float2((float)__ldg(p1 + 32 * m), (float)__ldg(p3 + 32 * m));
+                });
+            } else {                                                        // reflect padding at the clip edges
+                static_for<0, 32>([&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    int64_t sidx = s0 + 32 * m + lane;
+                    if (sidx < 0) sidx = -sidx;
+                    if (sidx >= a.L) sidx = 2 * (a.L - 1) - sidx;
+                    const TIn* p = xb + sidx;
+                    re[m] = make_float2((float)__ldg(p), (float)__ldg(p + 2 * a.stride_c));
+                    im[m] = make_float2((float)__ldg(p + a.stride_c), (float)__ldg(p + 3 * a.stride_c));
+                });
+            }
+        } else {
+            bool interior = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t sk = (int64_t)tk[k] * hop - 512;
+                interior = interior && vk[k] && sk >= 0 && sk + 1024 <= a.L;
+            }
+            if (interior) {
+                const TIn* p0 = xb + ck[0] * a.stride_c + ((int64_t)tk[0] * hop - 512) + lane;
+                const TIn* p1 = xb + ck[1] * a.stride_c + ((int64_t)tk[1] * hop - 512) + lane;
+                const TIn* p2 = xb + ck[2] * a.stride_c + ((int64_t)tk[2] * hop - 512) + lane;
+                const TIn* p3 = xb + ck[3] * a.stride_c + ((int64_t)tk[3] * hop - 512) + lane;
+                static_for<0, 32>([&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    re[m] = make_float2((float)__ldg(p0 + 32 * m), (float)__ldg(p2 + 32 * m));
+                    im[m] = make_float2((float)__ldg(p1 + 32 * m), (float)__ldg(p3 + 32 * m));
+                });
+            } else {                                                        // reflect padding at the clip edges / empty slots
+                auto edge = [&](int k, int m) -> float {
+                    if (!vk[k]) return 0.0f;
+                    int64_t sidx = (int64_t)tk[k] * hop - 512 + 32 * m + lane;
+                    if (sidx < 0) sidx = -sidx;
+                    if (sidx >= a.L) sidx = 2 * (a.L - 1) - sidx;
+                    return (float)__ldg(xb + ck[k] * a.stride_c + sidx);
+                };
+                static_for<0, 32>([&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    re[m] = make_float2(edge(0, m), edge(2, m));
+                    im[m] = make_float2(edge(1, m), edge(3, m));
+                });
+            }
         }
         PHASE_MARK(1);   // loads issued
         static_for<0, 8>([&](auto mi) {
@@ -206,27 +259,38 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 const float2 br = vadd(zi, pi), bi = vsub(pr, zr);          // (X1, X3)
                 const float2 p02 = __ffma2_rn(ai, ai, __fmul2_rn(ar, ar));
                 const float2 p13 = __ffma2_rn(bi, bi, __fmul2_rn(br, br));
-                const float2 i13 = vfmas(bi, ai.x, vmuls(br, ar.x));        // Re(conj(X0) X1), Re(conj(X0) X3)
-                const float i2 = fmaf(ai.x, ai.y, ar.x * ar.y);             // Re(conj(X0) X2)
-                const float s = fmaf(i13.y, i13.y, fmaf(i2, i2, i13.x * i13.x));
-                const float nrm = (s > 1e-37f ? s * rsqrt_ftz(s) : 0.0f) + eps;
-                const float inv = rcp_ftz(nrm);
-                if (kb < 16 || lane == 0) {
-                    float* q = R + 32 * kb + wofs[kb & 3];
-                    q[0 * kRowWords] = p02.x;
-                    q[1 * kRowWords] = p13.x;
-                    q[2 * kRowWords] = p02.y;
-                    q[3 * kRowWords] = p13.y;
-                    q[4 * kRowWords] = i13.x * inv;
-                    q[5 * kRowWords] = i2 * inv;
-                    q[6 * kRowWords] = i13.y * inv;
+                if constexpr (kIV) {
+                    const float2 i13 = vfmas(bi, ai.x, vmuls(br, ar.x));    // Re(conj(X0) X1), Re(conj(X0) X3)
+                    const float i2 = fmaf(ai.x, ai.y, ar.x * ar.y);         // Re(conj(X0) X2)
+                    const float s = fmaf(i13.y, i13.y, fmaf(i2, i2, i13.x * i13.x));
+                    const float nrm = (s > 1e-37f ? s * rsqrt_ftz(s) : 0.0f) + eps;
+                    const float inv = rcp_ftz(nrm);
+                    if (kb < 16 || lane == 0) {
+                        float* q = R + 32 * kb + wofs[kb & 3];
+                        q[0 * kRowWords] = p02.x;
+                        q[1 * kRowWords] = p13.x;
+                        q[2 * kRowWords] = p02.y;
+                        q[3 * kRowWords] = p13.y;
+                        q[4 * kRowWords] = i13.x * inv;
+                        q[5 * kRowWords] = i2 * inv;
+                        q[6 * kRowWords] = i13.y * inv;
+                    }
+                } else {
+                    if (kb < 16 || lane == 0) {
+                        float* q = R + 32 * kb + wofs[kb & 3];
+                        q[0 * kRowWords] = p02.x;
+                        q[1 * kRowWords] = p13.x;
+                        q[2 * kRowWords] = p02.y;
+                        q[3 * kRowWords] = p13.y;
+                    }
                 }
             });
         }
         __syncwarp();
 
         PHASE_MARK(6);   // pointwise
-        // ---------------- mel step 1: chunk walk of all seven rows, per-run partial sums (U, V) left in the rows
+        // ---------------- mel step 1: chunk walk of all rows, per-run partial sums (U, V) left in the rows
+        constexpr int NR = kIV ? kRows : 4;
         {
             float2 wv[17];
             const float4* wp = reinterpret_cast<const float4*>(wab_s + lane * kWabStride);
@@ -237,9 +301,9 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 wv[2 * i + 1] = make_float2(v.z, v.w);
             }
             wv[16] = *reinterpret_cast<const float2*>(wab_s + lane * kWabStride + 32);
-            float q[kRows][17];
+            float q[NR][17];
 #pragma unroll
-            for (int f = 0; f < kRows; ++f) {
+            for (int f = 0; f < NR; ++f) {
                 const float* row = R + f * kRowWords;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -249,11 +313,11 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 q[f][16] = lane == 31 ? row[512] : 0.0f;
             }
             __syncwarp();                                                   // everyone holds its bins: rows may be overwritten
-            if (lane < kRows) reinterpret_cast<float2*>(R + lane * kRowWords)[kZeroRun] = make_float2(0.f, 0.f);
-            float2 acc[kRows];
+            if (lane < NR) reinterpret_cast<float2*>(R + lane * kRowWords)[kZeroRun] = make_float2(0.f, 0.f);
+            float2 acc[NR];
             float2* po = reinterpret_cast<float2*>(R) + g0;
 #pragma unroll
-            for (int f = 0; f < kRows; ++f) acc[f] = vmuls(wv[0], q[f][0]);
+            for (int f = 0; f < NR; ++f) acc[f] = vmuls(wv[0], q[f][0]);
             // branch-free: where a new run starts the finished pair is stored and the accumulator restarts
             // (acc * keep with keep = 0); one FMUL2 + one FFMA2 + one predicated store per bin and row
             static_for<1, 17>([&](auto ji) {
@@ -261,21 +325,31 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 const bool start = (runmask >> j) & 1u;
                 const float keep = start ? 0.0f : 1.0f;
 #pragma unroll
-                for (int f = 0; f < kRows; ++f) {
+                for (int f = 0; f < NR; ++f) {
                     if (start) po[f * (kRowWords / 2)] = acc[f];
                     acc[f] = __ffma2_rn(wv[j], make_float2(q[f][j], q[f][j]), vmuls(acc[f], keep));
                 }
                 po += start ? 1 : 0;
             });
 #pragma unroll
-            for (int f = 0; f < kRows; ++f) po[f * (kRowWords / 2)] = acc[f];
+            for (int f = 0; f < NR; ++f) po[f * (kRowWords / 2)] = acc[f];
         }
         __syncwarp();
 
         PHASE_MARK(7);   // mel walk
         // ---------------- mel step 2: band per lane, out[m] = sum V(runs of segment m) + sum U(runs of segment m+1)
         {
-            float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
+            // destination of row f (one 64-float line of the output per row): kIV: channels 0-3 and the three
+            // IV channels of frame t; log-mel only: (channel, frame) of slot f, if that slot holds a job
+            float* const ob = a.out + ((int64_t)b * a.Cout) * ch_stride + (kIV ? (int64_t)t * M : 0);
+            auto emit = [&](int f, int m, float v) {
+                if (f < 4) v = 3.01029995663981195f * __log2f(fmaxf(v, amin));   // 10*log10(max(v, amin))
+                if constexpr (kIV) {
+                    ob[(f < 4 ? f : a.C + f - 4) * ch_stride + m] = v;
+                } else {
+                    if (vk[f & 3]) ob[ck[f & 3] * ch_stride + (int64_t)tk[f & 3] * M + m] = v;
+                }
+            };
             if (M <= 64) {
                 // fixed slots: <= 4 runs per segment, run numbers held packed in registers (absent -> the zero run);
                 // all loads are issued up front (a data-dependent slot count was measured 2.4 % slower)
@@ -286,9 +360,9 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                         const int m = lane + 32 * r;
                         if (m < M) {
                             const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
-                            float v[kRows];
+                            float v[NR];
 #pragma unroll
-                            for (int f = 0; f < kRows; ++f) {
+                            for (int f = 0; f < NR; ++f) {
                                 const float* rowp = R + f * kRowWords;
                                 const float v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
                                 const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
@@ -302,10 +376,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                                 }
                             }
 #pragma unroll
-                            for (int f = 0; f < 4; ++f)                          // 10*log10(max(v, amin))
-                                ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
-#pragma unroll
-                            for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
+                            for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
                         }
                     }
                 };
@@ -314,22 +385,19 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 const float2* P = reinterpret_cast<const float2*>(R);
                 for (int m = lane; m < M; m += 32) {
                     const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
-                    float v[kRows];
+                    float v[NR];
 #pragma unroll
-                    for (int f = 0; f < kRows; ++f) v[f] = 0.0f;
+                    for (int f = 0; f < NR; ++f) v[f] = 0.0f;
                     for (int g = ga; g < gb; ++g) {
 #pragma unroll
-                        for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].y;
+                        for (int f = 0; f < NR; ++f) v[f] += P[f * (kRowWords / 2) + g].y;
                     }
                     for (int g = gb; g < gc; ++g) {
 #pragma unroll
-                        for (int f = 0; f < kRows; ++f) v[f] += P[f * (kRowWords / 2) + g].x;
+                        for (int f = 0; f < NR; ++f) v[f] += P[f * (kRowWords / 2) + g].x;
                     }
 #pragma unroll
-                    for (int f = 0; f < 4; ++f)
-                        ob[f * ch_stride + m] = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
-#pragma unroll
-                    for (int f = 4; f < kRows; ++f) ob[(a.C + f - 4) * ch_stride + m] = v[f];
+                    for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
                 }
             }
         }
@@ -364,13 +432,13 @@ bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin) {
 
 int foa_iv2_frames_per_tile() { return iv2_warps(); }
 
-template <int W, typename TIn>
+template <int W, typename TIn, bool kIV>
 static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
     const size_t smem = iv2_smem_bytes<W>(pd);
-    cudaError_t e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
-    foa_iv2_kernel<W, TIn><<<gx, W * 32, smem, st>>>(a, pd);
+    foa_iv2_kernel<W, TIn, kIV><<<gx, W * 32, smem, st>>>(a, pd);
     return cudaGetLastError();
 }
 
@@ -383,11 +451,18 @@ extern "C" void seld_dev_phase_cycles(unsigned long long* out, int reset) {
 #endif
 
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
-    if (a.in_i16) return iv2_launch_t<8, int16_t>(a, pd, sm_count, st);
+    if (a.in_i16) return iv2_launch_t<8, int16_t, true>(a, pd, sm_count, st);
     switch (iv2_warps()) {
-        case 12: return iv2_launch_t<12, float>(a, pd, sm_count, st);
-        default: return iv2_launch_t<8, float>(a, pd, sm_count, st);
+        case 12: return iv2_launch_t<12, float, true>(a, pd, sm_count, st);
+        default: return iv2_launch_t<8, float, true>(a, pd, sm_count, st);
     }
+}
+
+// log-mel only, any channel count: channels [a.c_lo, a.C) of every clip; a.tiles_per_clip counts tiles of
+// 8 warps x 4 (frame, channel) jobs
+int foa_lm4_jobs_per_tile() { return 8 * 4; }
+cudaError_t foa_lm4_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
+    return iv2_launch_t<8, float, false>(a, pd, sm_count, st);
 }
 
 }  // namespace seld

@@ -52,6 +52,8 @@ cudaError_t foa_launch(bool iv, const FoaArgs& a, const PlanDev& pd, int sm_coun
 bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin);
 int foa_iv2_frames_per_tile();
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
+int foa_lm4_jobs_per_tile();
+cudaError_t foa_lm4_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
 
 // third-generation kernel: two warps per frame (seld_foa_iv3.cu)
 bool foa_iv3_supported(const PlanDev& pd, size_t smem_optin);
