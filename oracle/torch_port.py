@@ -33,21 +33,14 @@ def _amp2db(x):
     return x_db
 
 
-def intensityvector(inp, melW):
-    # feature.py:93-117
-    sig_real, sig_imag = inp[0], inp[1]
-    Pref_real, Pref_imag = sig_real[:, 0, ...], sig_imag[:, 0, ...]
-    Px_real, Px_imag = sig_real[:, 1, ...], sig_imag[:, 1, ...]
-    Py_real, Py_imag = sig_real[:, 2, ...], sig_imag[:, 2, ...]
-    Pz_real, Pz_imag = sig_real[:, 3, ...], sig_imag[:, 3, ...]
-    IVx = Pref_real * Px_real + Pref_imag * Px_imag
-    IVy = Pref_real * Py_real + Pref_imag * Py_imag
-    IVz = Pref_real * Pz_real + Pref_imag * Pz_imag
-    normal = torch.sqrt(IVx ** 2 + IVy ** 2 + IVz ** 2) + EPS
-    IVx_mel = torch.matmul(IVx / normal, melW)
-    IVy_mel = torch.matmul(IVy / normal, melW)
-    IVz_mel = torch.matmul(IVz / normal, melW)
-    return torch.stack([IVx_mel, IVy_mel, IVz_mel], dim=1)
+def intensityvector(spec_re, spec_im, fb):
+    """(B, >=4, T, F) real / imaginary parts -> (B, 3, T, M).  Same operations, in the same order, as
+    feature.py:101-115: three real cross terms with channel 0, their Euclidean norm + eps, three divisions,
+    three (T, F) @ (F, M) products, stacked."""
+    w_re, w_im = spec_re[:, 0], spec_im[:, 0]
+    cross = [w_re * spec_re[:, j] + w_im * spec_im[:, j] for j in (1, 2, 3)]
+    norm = torch.sqrt(cross[0] ** 2 + cross[1] ** 2 + cross[2] ** 2) + EPS
+    return torch.stack([torch.matmul(c / norm, fb) for c in cross], dim=1)
 
 
 @torch.no_grad()
@@ -58,7 +51,7 @@ def logmel_iv(x, window, fb, n_fft, hop):
     X = _spectrogram(x, window, n_fft, hop)
     mel = _mel_scale(torch.abs(X) ** 2, fb)
     logmel = _amp2db(mel).transpose(-1, -2)
-    iv = intensityvector([X.real.transpose(-1, -2), X.imag.transpose(-1, -2)], fb)
+    iv = intensityvector(X.real.transpose(-1, -2), X.imag.transpose(-1, -2), fb)
     return torch.cat((logmel, iv), dim=1)
 
 

@@ -1,17 +1,19 @@
-"""Factory seam of the reference: /root/reference/src/utils/config.py:24-32."""
+"""Factory seam: the one place the reference wires its extractor
+(/root/reference/src/utils/config.py:24-32, `get_afextractor(cfg)` keyed on
+`cfg['data']['audio_feature']`).  Same name, same argument, same return convention (an nn.Module, or
+None for feature kinds that have no on-line extractor)."""
 from . import feature
+
+# audio_feature value -> extractor class.  'logmelgcc' is an addition: the reference returns None for it and
+# computes MIC features offline (src/preproc/preprocess.py:525-563).
+_EXTRACTORS = {
+    'logmelIV': feature.LogmelIV_Extractor,
+    'logmel': feature.Logmel_Extractor,
+    'logmelgcc': feature.LogmelGCC_Extractor,
+}
 
 
 def get_afextractor(cfg):
-    """ Get audio feature extractor."""
-    if cfg['data']['audio_feature'] == 'logmelIV':
-        afextractor = feature.LogmelIV_Extractor(cfg)
-    elif cfg['data']['audio_feature'] == 'logmel':
-        afextractor = feature.Logmel_Extractor(cfg)
-    elif cfg['data']['audio_feature'] == 'logmelgcc':
-        # the reference returns None here (MIC features come from its offline numpy class);
-        # this build adds the on-GPU module for the same features
-        afextractor = feature.LogmelGCC_Extractor(cfg)
-    else:
-        afextractor = None
-    return afextractor
+    """Audio feature extractor for this config, or None (e.g. 'salsalite')."""
+    cls = _EXTRACTORS.get(cfg['data']['audio_feature'])
+    return cls(cfg) if cls is not None else None
