@@ -44,47 +44,75 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a background thread (one
+    query every ~2 ms); falls back to polling `nvidia-smi` (the B200_PROFILING.md clocks line)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop_flag = False
         self.thread = None
+        self.source = 'nvml'
 
-    def _loop(self):
+    def _loop_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(vis.split(',')[self.idx]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else self.idx
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown, 'hw_thermal_slowdown': nv.nvmlClocksEventReasonHwThermalSlowdown,
+                'sw_thermal_slowdown': nv.nvmlClocksEventReasonSwThermalSlowdown, 'sw_power_cap': nv.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop_flag:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(mx))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(0.002)
+
+    def _loop_smi(self):
+        self.source = 'nvidia-smi'
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
-                    self.rows.append([v.strip() for v in line.split(',')])
+                    r = [v.strip() for v in line.split(',')]
+                    self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+                    for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                        if v.lower().startswith('active'):
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.05)
+
+    def _loop(self):
+        try:
+            self._loop_nvml()
+        except Exception:
+            self._loop_smi()
 
     def start(self):
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
 
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.first = len(self.sm)
+
     def stop(self):
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=10)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        first = getattr(self, 'first', 0)
+        sm = self.sm[first:] or self.sm
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                'reasons': sorted(self.reasons), 'samples': len(sm), 'source': self.source}
 
 
 def cpu_port_throughput(batch, min_seconds, max_calls, threads):
@@ -248,6 +276,8 @@ def run_ours(args):
     launches0 = _abi.lib().seld_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    if rank == 0:
+        sampler.mark()
     ev[0].record()
     for i in range(args.steps):
         y = ext(x)
