@@ -115,6 +115,20 @@ class ClockSampler:
                 'reasons': sorted(self.reasons), 'samples': len(sm), 'source': self.source}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads to the CPUs closest to its GPU (NVML's ideal affinity), so page-locked
+    buffers are first-touched on that NUMA node and host<->device copies do not cross sockets."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(vis.split(',')[local_rank]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else local_rank
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:
+        return False
+
+
 def cpu_port_throughput(batch, min_seconds, max_calls, threads):
     """The reference's CPU path (oracle/torch_port.py: same torch.stft / matmul calls as the
     reference makes through torchaudio) on the host cores.  Returns (audio-s/s, calls, seconds)."""
@@ -185,6 +199,7 @@ def run_extra(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     if args.workload == 'cfg3':
         sr, hop, Lw, Cin, name = 24000, 240, 240000, 4, 'cfg3: MIC log-mel+GCC-PHAT, batch 64 x 10 s x 4 mics @ 24 kHz per GPU -> (64,10,1000,64)'
@@ -251,7 +266,9 @@ def run_ours(args):
         raise RuntimeError('bench.py needs a CUDA device: the hot path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    bind_to_gpu_numa_node(local_rank)       # pinned host buffers (e2e) then live on the GPU's own NUMA node
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')    # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     B = args.batch
     ext = pb.get_afextractor(CFG).to(dev)
@@ -329,6 +346,10 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get('foa_iv2_kernel_bytes_per_launch')
             except Exception:
                 traffic = None
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))       # the CPU baseline gets every host core back
+        except Exception:
+            pass
         cpu_threads = os.cpu_count() or 1
         cpu_val, cpu_calls, cpu_secs = cpu_port_throughput(8, args.cpu_seconds, 200, cpu_threads)
         out = {
