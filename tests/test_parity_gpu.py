@@ -284,3 +284,24 @@ def test_other_configurations_against_oracle():
         assert_blocks_close(y, ref, 4, what='sr=%d hop=%d M=%d' % (sr, hop, n_mels))
     with pytest.raises(_abi.SeldError):                  # n_fft other than 1024 is outside the kernels
         pb.LogmelIV_Extractor(make_cfg(24000, 240, nfft=512)).cuda()(torch.zeros(1, 4, 2400, device='cuda'))
+
+
+def test_fuzz_shapes_against_oracle():
+    """Seeded sweep over awkward shapes: shortest legal clip (L = 513), single-frame outputs, hops that are
+    odd / larger than the window, batch sizes around the tile size, unaligned lengths."""
+    from oracle import seld_oracle as so, synth
+    rng = np.random.default_rng(2024)
+    cases = [(1, 513, 240), (1, 514, 513), (3, 1023, 1000), (2, 2047, 333), (9, 700, 77), (17, 1500, 240), (1, 30001, 241)]
+    for _ in range(6):
+        cases.append((int(rng.integers(1, 12)), int(rng.integers(513, 6000)), int(rng.integers(16, 1500))))
+    for i, (B, L, hop) in enumerate(cases):
+        for kind in ('logmelIV', 'logmel'):
+            C = 4 if kind == 'logmelIV' else int(rng.integers(1, 7))
+            cfg = make_cfg(24000, hop, 'hann', kind)
+            ext = (pb.LogmelIV_Extractor if kind == 'logmelIV' else pb.Logmel_Extractor)(cfg).cuda()
+            x = synth.white(900 + i, B, C, L)
+            y = _run(ext, x)
+            w, fb = ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy()
+            ref = (so.logmel_iv if kind == 'logmelIV' else so.logmel)(x, w, fb, 1024, hop, np.float64)
+            assert y.shape == ref.shape == (B, C + (3 if kind == 'logmelIV' else 0), 1 + L // hop, 64)
+            assert_blocks_close(y, ref, C, what='%s B=%d L=%d hop=%d C=%d' % (kind, B, L, hop, C))
