@@ -130,12 +130,12 @@ class LogmelIV_Extractor(_ExtractorBase):
     _extra_ch = 3
 
 
-    def forward_host(self, x, out=None, device=None, chunk_clips=0):
+    def forward_host(self, x, out=None, device=None, chunk_clips=0, synchronize=True):
         """Host-buffer form of forward(): x is a CPU float32 tensor (B, C, L) (page-locked for
         full overlap); returns a page-locked CPU tensor (B, C+3, T, n_mels).  Chunks of the batch
         are copied in, transformed and copied out on three overlapping streams inside
-        libseldfeat.so (seld_logmel_iv_f32_host).  The result is complete once the current stream
-        of `device` has been synchronised."""
+        libseldfeat.so (seld_logmel_iv_f32_host).  With synchronize=False the call only enqueues:
+        the result is complete once the current stream of `device` has been synchronised."""
         if x.ndim != 3:
             raise ValueError("x shape must be (batch_size, num_channels, data_length)\n \
                             Now it is {}".format(x.shape))
@@ -154,6 +154,8 @@ class LogmelIV_Extractor(_ExtractorBase):
         name = 'seld_logmel_iv_i16_host' if x.dtype == torch.int16 else 'seld_logmel_iv_f32_host'
         code = getattr(_abi.lib(), name)(plan.handle, x.data_ptr(), B, C, L, out.data_ptr(), int(chunk_clips), stream)
         _abi.check(code, name)
+        if synchronize:
+            torch.cuda.current_stream(dev).synchronize()
         return out
 
 
