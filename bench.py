@@ -253,6 +253,77 @@ def run_extra(args):
         dist.destroy_process_group()
 
 
+def run_epilogue(args):
+    """SURVEY 8f-1 (extra measurement, 1 GPU): the backbone-input stage on the cfg2 feature map
+    (64, 7, 1001, 64) -> (64, 7, 256, 256): fused scalar + fold, the in-place scalar alone, and the
+    reference's own op chain (accdoa.py:222-227 + htsat.py:493-511) run by torch on the same GPU."""
+    import torch
+    import pseldnets_b200 as pb
+    from pseldnets_b200 import _abi
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    B, C, T, M, S = args.batch, 7, 1001, 64, 256
+    g = torch.Generator(device=dev).manual_seed(1238)
+    n_maps = 4                                   # 4 x 115 MB of input in rotation: each step reads a map that left L2
+    maps = [40.0 * torch.rand(B, C, T, M, device=dev, generator=g) - 50.0 for _ in range(n_maps)]
+    scalar = torch.nn.ModuleList([torch.nn.BatchNorm2d(M) for _ in range(C)]).to(dev).eval()
+    for bn in scalar:
+        bn.running_mean.copy_(30.0 * torch.rand(M, device=dev, generator=g) - 40.0)
+        bn.running_var.copy_(50.0 * torch.rand(M, device=dev, generator=g) + 1.0)
+    sp = pb.ScalarParams(scalar)
+
+    def reference_chain(x):
+        with torch.no_grad():
+            x = x.transpose(1, 3)
+            for nch in range(x.shape[-1]):
+                x[..., [nch]] = scalar[nch](x[..., [nch]])
+            x = x.transpose(1, 3)
+            x = torch.nn.functional.pad(x, (0, 0, 0, 4 * S - T))
+            x = x.permute(0, 1, 3, 2).contiguous()
+            x = x.reshape(B, C, M, 4, S).permute(0, 1, 3, 2, 4).contiguous()
+            return x.reshape(B, C, 4 * M, S)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(maps[i % n_maps])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(maps[i % n_maps])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0 = _abi.lib().seld_launch_count()
+    sampler.mark()
+    ms_fused = timed(lambda x: pb.scalar_wav2img(x, sp, S), args.steps, warm)
+    n_launch = int(_abi.lib().seld_launch_count() - l0)
+    ms_scalar = timed(lambda x: pb.apply_scalar(x, sp), args.steps, warm)
+    clocks = sampler.stop()
+    ms_ref = timed(reference_chain, max(3, args.steps // 10), 3)
+    peak, peak_src = measured_peaks()
+    in_b, out_b = B * C * T * M * 4, B * C * S * S * 4
+    algo = in_b + out_b
+    print(json.dumps({
+        'metric': 'audio-seconds/sec (backbone-input stage: scalar + reshape_wav2img)', 'value': B * CLIP_S / (ms_fused * 1e-3),
+        'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_fused, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '8f-1: eval BatchNorm scalar + HTS-AT fold of the cfg2 feature map (%d,7,1001,64) -> (%d,7,256,256); '
+                               'inputs rotate over %d maps (%d MB > L2)' % (B, B, n_maps, n_maps * in_b // 2**20)},
+        'roofline': {'bound': 'hbm', 'achieved': algo / (ms_fused * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                     'frac': algo / (ms_fused * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_step': algo, 'kernel': 'seld::epi::scalar_wav2img_kernel'},
+        'scalar_in_place': {'ms_per_step': ms_scalar, 'achieved_gbs': 2 * in_b / (ms_scalar * 1e-3) / 1e9,
+                            'frac': 2 * in_b / (ms_scalar * 1e-3) / 1e9 / peak, 'kernel': 'seld::epi::scalar_kernel'},
+        'torch_op_chain_same_gpu': {'ms_per_step': ms_ref, 'speedup': ms_ref / ms_fused,
+                                    'what': 'accdoa.py:222-227 loop + htsat.py:493-511 in torch eager'},
+        'gpu_launches': n_launch, 'clocks': clocks}))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -383,7 +454,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='clips per GPU per step (cfg2: 64)')
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'],
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'wav2img'],
                     help='cfg2 = BASELINE metric (default); cfg3 = MIC log-mel+GCC B=64; cfg4 = L3DAS22 dual-FOA '
                          '8 ch 32 kHz, global batch 128 sharded by clip (extra measurements, not the headline)')
     ap.add_argument('--cpu-seconds', type=float, default=10.0, help='bound on the cpu_baseline sample')
@@ -391,6 +462,8 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'wav2img':
+        run_epilogue(args)
     elif args.workload != 'cfg2':
         run_extra(args)
     else:

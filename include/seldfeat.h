@@ -87,6 +87,27 @@ int seld_logmel_gcc_f32(const seld_plan* plan, const float* x, int64_t B, int C,
                         int64_t stride_b, int64_t stride_c, float top_db, float* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Backbone-input stage: what every backbone does first with the feature map.
+ *
+ * seld_scalar_f32: the per-channel eval-mode BatchNorm2d "scalar" loop of the backbones
+ * (src/models/accdoa.py:222-227, 318-321; src/models/einv2.py:106-109, 292-295), in place on
+ * x (B, C, T, M) contiguous device fp32.  mean / var / weight / bias are (C, M) device fp32: row c
+ * holds running_mean / running_var / weight / bias of scalar[c]; weight and bias may be null
+ * (affine=False); mean == var == null means "no scalar" (no-op).  Rounds exactly like torch's CPU
+ * kernel: a = weight / sqrt(var + eps) [as w * (1 / sqrt)], b = fma(-mean, a, bias), y = fma(x, a, b).
+ * Training-mode batch statistics are not part of this path.  M % 4 == 0, 16-byte aligned pointers.
+ *
+ * seld_scalar_wav2img_f32: the same map fused with HTSAT_Swin_Transformer.reshape_wav2img
+ * (src/models/components/htsat.py:493-511): x (B, C, T, M) -> img (B, C, spec_size, spec_size),
+ * img[b][c][k*M + m][t] = y[b][c][k*spec_size + t][m] for k < spec_size / M; frames past T are zero
+ * (F.pad after the scalar), frames past (spec_size / M) * spec_size are dropped (negative pad).
+ * x is not modified.  spec_size % M == 0 (else SELD_EINVAL), spec_size % 4 == 0. */
+int seld_scalar_f32(float* x, int64_t B, int C, int64_t T, int M, const float* mean, const float* var,
+                    const float* weight, const float* bias, float eps, void* stream);
+int seld_scalar_wav2img_f32(const float* x, int64_t B, int C, int64_t T, int M, int spec_size,
+                            const float* mean, const float* var, const float* weight, const float* bias,
+                            float eps, float* img, void* stream);
+
 /* Kernels enqueued by this library since load (all entry points, all plans). */
 uint64_t seld_launch_count(void);
 /* cudaError_t of the most recent failing runtime call on this thread (0 if none). */

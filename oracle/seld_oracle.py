@@ -9,6 +9,13 @@ algorithm of /root/reference/src/utils/feature.py:
   * logmel_gcc()  <- Features_Extractor_MIC._spectrogram/_get_logmel_spectrogram/_get_gcc
                      (feature.py:146-175) assembled as preprocess.py:546-556
 
+and the first stage of the backbones that consume the feature map:
+
+  * scalar_eval()    <- the per-channel eval-mode BatchNorm2d "scalar" loop
+                        (src/models/accdoa.py:222-227, 318-321; einv2.py:106-109, 292-295)
+  * reshape_wav2img()<- HTSAT_Swin_Transformer.reshape_wav2img
+                        (src/models/components/htsat.py:493-511)
+
 The arithmetic of those functions lives in third-party packages that are not vendored in the
 reference tree: torchaudio==2.2.1 (transforms.Spectrogram / MelScale / AmplitudeToDB),
 torch==2.2.1 (torch.stft, matmul), librosa==0.10.1 (stft, filters.mel, power_to_db) and
@@ -20,7 +27,9 @@ itself executed in the build container: tests/golden/make_golden.py imports the 
 /root/reference/src/utils/feature.py, runs it on seeded inputs and commits the outputs as
 tests/golden/*.npz; tests/test_oracle.py checks this file against those vectors.  The MIC path
 needs librosa, which is not installable offline -> its restatement is "parity unpinned"
-(checked only against an independent scipy evaluation and its own fp64 mode).
+(checked only against an independent scipy evaluation and its own fp64 mode).  The two
+backbone-input functions are pinned by tests/golden/make_golden_epilogue.py, which executes the
+reference's own reshape_wav2img and torch.nn.BatchNorm2d loop (tests/golden/epilogue.npz).
 
 `dtype=np.float32` follows the reference's fp32 arithmetic stage by stage (the FFT itself is
 numpy/pocketfft in fp32); `dtype=np.float64` is the "truth" evaluation used to bound the
@@ -131,3 +140,48 @@ def logmel_gcc(x, window, mel_bank, n_fft, hop, n_mels=None, top_db=80.0, dtype=
             cc = np.fft.irfft(ph, n=n_fft, axis=-1)
             feats.append(np.concatenate((cc[..., -M // 2:], cc[..., :M // 2]), axis=-1))
     return np.stack(feats, axis=1).astype(dtype)
+
+
+def _fma32(a, b, c):
+    """fp32 fused multiply-add: the product of two fp32 numbers is exact in fp64."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def scalar_eval(x, mean, var, weight, bias, eps=1e-5):
+    """Eval-mode "scalar" of the backbones: x (B, C, T, M) -> same shape.
+
+    accdoa.py:222-227: x is viewed as (B, M, T, C) and channel c goes through its own
+    BatchNorm2d(M): y = (x - running_mean[c, m]) / sqrt(running_var[c, m] + eps) * weight[c, m]
+    + bias[c, m].  Evaluated the way torch's CPU kernel rounds it (bit-exact against
+    tests/golden/epilogue.npz): one multiplier and one offset per (c, m),
+        a = weight * (1 / sqrt(var + eps)),  b = fma(-mean, a, bias),  y = fma(x, a, b).
+    mean / var / weight / bias: (C, M).  fp64 input: plain double arithmetic.
+    """
+    x = np.asarray(x)
+    dt = x.dtype.type
+    inv = dt(1.0) / np.sqrt(np.asarray(var, x.dtype) + dt(eps))
+    a = np.asarray(weight, x.dtype) * inv
+    a4 = a[None, :, None, :]
+    if x.dtype == np.float32:
+        b = _fma32(-np.asarray(mean, np.float32), a, np.asarray(bias, np.float32))
+        return _fma32(x, np.broadcast_to(a4, x.shape), np.broadcast_to(b[None, :, None, :], x.shape))
+    b = np.asarray(bias, x.dtype) - np.asarray(mean, x.dtype) * a
+    return x * a4 + b[None, :, None, :]
+
+
+def reshape_wav2img(x, spec_size=256):
+    """htsat.py:493-511: x (B, C, T, M) -> (B, C, spec_size, spec_size) "image".
+
+    freq_ratio r = spec_size // M (htsat.py:442); the time axis is zero-padded (or, when longer,
+    cropped: F.pad with a negative amount) to r * spec_size frames and cut into r consecutive
+    pieces that are stacked along the mel axis:  img[b, c, k*M + m, t] = x[b, c, k*spec_size + t, m].
+    """
+    x = np.asarray(x)
+    B, C, T, M = x.shape
+    r = spec_size // M
+    target_T = spec_size * r
+    xp = np.zeros((B, C, target_T, M), dtype=x.dtype)
+    n = min(T, target_T)
+    xp[:, :, :n] = x[:, :, :n]
+    return np.ascontiguousarray(xp.reshape(B, C, r, target_T // r, M).transpose(0, 1, 2, 4, 3)).reshape(
+        B, C, r * M, target_T // r)

@@ -52,3 +52,22 @@ def half_silent(seed, B, C, L, scale=0.1):
     x = white(seed, B, C, L, scale)
     x[..., L // 2:] = 0.0
     return x
+
+
+def feature_like(seed, B, C, T, M):
+    """Stand-in for an extracted feature map: dB-like values in the leading channels, [-1, 1) after."""
+    u = uniform(seed, (B, C, T, M))
+    x = u.copy()
+    n_db = max(1, C - 3)
+    x[:, :n_db] = np.float32(40.0) * u[:, :n_db] - np.float32(50.0)
+    return x.astype(np.float32)
+
+
+def scalar_params(seed, C, M):
+    """Running statistics / affine terms of C BatchNorm2d(M) "scalar" modules: four (C, M) fp32 arrays."""
+    u = uniform(seed, (4, C, M))
+    mean = np.float32(30.0) * u[0] - np.float32(20.0)
+    var = np.float32(50.0) * (u[1] + np.float32(1.0)) + np.float32(0.01)
+    weight = np.float32(1.0) + np.float32(0.5) * u[2]
+    bias = np.float32(0.3) * u[3]
+    return (mean.astype(np.float32), var.astype(np.float32), weight.astype(np.float32), bias.astype(np.float32))

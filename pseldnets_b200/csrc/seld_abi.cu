@@ -416,6 +416,68 @@ extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B
     return SELD_OK;
 }
 
+// ---- backbone-input stage (stateless: no plan)
+static int current_sm_count(int* sm) {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    int v = dev < 64 ? cache[dev].load(std::memory_order_relaxed) : 0;
+    if (v == 0) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return cuda_fail(e);
+        if (dev < 64) cache[dev].store(v, std::memory_order_relaxed);
+    }
+    *sm = v;
+    return SELD_OK;
+}
+
+static int check_scalar(const float* mean, const float* var, const float* weight, const float* bias, seld::ScalarArgs* s,
+                        float eps) {
+    if ((mean == nullptr) != (var == nullptr)) return SELD_EINVAL;      // statistics come as a pair
+    if (!mean && (weight || bias)) return SELD_EINVAL;
+    const uintptr_t al = (uintptr_t)mean | (uintptr_t)var | (uintptr_t)weight | (uintptr_t)bias;
+    if (al & 15) return SELD_EUNSUPPORTED;
+    s->mean = mean; s->var = var; s->weight = weight; s->bias = bias; s->eps = eps;
+    return SELD_OK;
+}
+
+extern "C" int seld_scalar_f32(float* x, int64_t B, int C, int64_t T, int M, const float* mean, const float* var,
+                               const float* weight, const float* bias, float eps, void* stream) {
+    if (B < 0 || C < 1 || T < 1 || M < 1) return SELD_EINVAL;
+    if (M % 4 != 0 || T > INT32_MAX) return SELD_EUNSUPPORTED;
+    seld::ScalarArgs s;
+    if (int rc = check_scalar(mean, var, weight, bias, &s, eps)) return rc;
+    if (B == 0 || !mean) return SELD_OK;                                // nothing to do
+    if (!x) return SELD_EINVAL;
+    if ((uintptr_t)x & 15) return SELD_EUNSUPPORTED;
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    cudaError_t e = seld::scalar_launch(x, s, B, C, (int)T, M, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
+extern "C" int seld_scalar_wav2img_f32(const float* x, int64_t B, int C, int64_t T, int M, int spec_size,
+                                       const float* mean, const float* var, const float* weight, const float* bias,
+                                       float eps, float* img, void* stream) {
+    if (B < 0 || C < 1 || T < 1 || M < 1 || spec_size < 1) return SELD_EINVAL;
+    if (spec_size % M != 0) return SELD_EINVAL;                         // htsat.py:442,506: the fold needs spec_size = r * M
+    if (M % 4 != 0 || spec_size % 4 != 0 || T > INT32_MAX) return SELD_EUNSUPPORTED;
+    seld::ScalarArgs s;
+    if (int rc = check_scalar(mean, var, weight, bias, &s, eps)) return rc;
+    if (B == 0) return SELD_OK;
+    if (!x || !img) return SELD_EINVAL;
+    if (((uintptr_t)x | (uintptr_t)img) & 15) return SELD_EUNSUPPORTED;
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    cudaError_t e = seld::scalar_wav2img_launch(x, img, s, B, C, (int)T, M, spec_size, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
 extern "C" uint64_t seld_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int seld_last_cuda_error(void) { return g_last_cuda; }
 

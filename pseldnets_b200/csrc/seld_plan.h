@@ -67,4 +67,17 @@ int mic_frames_per_tile();
 cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float top_db, bool use_top_db,
                        int sm_count, cudaStream_t st);
 
+// backbone-input stage (seld_epilogue.cu): eval-mode BatchNorm "scalar" terms, each (C, M) on the device;
+// mean == nullptr means "no scalar" (identity)
+struct ScalarArgs {
+    const float* mean;
+    const float* var;
+    const float* weight;   // nullptr: 1
+    const float* bias;     // nullptr: 0
+    float eps;
+};
+cudaError_t scalar_launch(float* x, const ScalarArgs& s, int64_t B, int C, int T, int M, int sm_count, cudaStream_t st);
+cudaError_t scalar_wav2img_launch(const float* x, float* img, const ScalarArgs& s, int64_t B, int C, int T, int M, int S,
+                                  int sm_count, cudaStream_t st);
+
 }  // namespace seld

@@ -137,3 +137,44 @@ def test_segment_index_matches_reference_cases():
     for x_len, ch, hp in ((5, 10, 5), (20, 10, 5), (22, 10, 5), (23, 10, 10), (26, 10, 10), (415200, 240000, 12000)):
         for flag in (False, True):
             assert tuple(map(list, ref_si(np.zeros((1, x_len)), ch, hp, flag))) == tuple(map(list, inf.segment_index(x_len, ch, hp, flag)))
+
+
+def test_scalar_params_host_logic():
+    """ScalarParams stacks the reference's `scalar` ModuleList; everything that is not eval-mode
+    BatchNorm with running statistics is refused, and the compute calls refuse CPU tensors."""
+    C, M = 3, 8
+    scalar = torch.nn.ModuleList([torch.nn.BatchNorm2d(M) for _ in range(C)])
+    for c, bn in enumerate(scalar):
+        bn.running_mean.fill_(float(c))
+        bn.weight.data.fill_(2.0 + c)
+    with pytest.raises(RuntimeError):
+        pb.ScalarParams(scalar)                              # still in training mode
+    sp = pb.ScalarParams(scalar.eval())
+    assert (sp.C, sp.M) == (C, M) and sp.eps == 1e-5
+    assert torch.equal(sp.mean[:, 0], torch.arange(3.0)) and torch.equal(sp.weight[:, 0], torch.tensor([2.0, 3.0, 4.0]))
+    assert sp.var.shape == sp.bias.shape == (C, M)
+    na = pb.ScalarParams(torch.nn.ModuleList([torch.nn.BatchNorm2d(M, affine=False)]).eval())
+    assert na.weight is None and na.bias is None and na.pointers()[2:] == (0, 0)
+    with pytest.raises(RuntimeError):
+        pb.ScalarParams(torch.nn.ModuleList([torch.nn.BatchNorm2d(M, track_running_stats=False)]).eval())
+    with pytest.raises(ValueError):
+        pb.ScalarParams(torch.nn.ModuleList([torch.nn.BatchNorm2d(M, eps=1e-3), torch.nn.BatchNorm2d(M)]).eval())
+    x = torch.zeros(1, C, 5, M)
+    with pytest.raises(RuntimeError):
+        pb.apply_scalar(x, sp)                               # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        pb.reshape_wav2img(x, 8)
+    with pytest.raises(ValueError):
+        pb.reshape_wav2img(x[0], 8)
+
+
+def test_epilogue_abi_argument_checks_without_gpu():
+    l = _abi.lib()
+    assert l.seld_scalar_f32(None, 1, 7, 100, 64, None, None, None, None, 1e-5, None) == _abi.SELD_OK   # no scalar: no-op
+    assert l.seld_scalar_f32(None, 1, 0, 100, 64, None, None, None, None, 1e-5, None) == _abi.SELD_EINVAL
+    assert l.seld_scalar_f32(None, 1, 7, 100, 62, None, None, None, None, 1e-5, None) == _abi.SELD_EUNSUPPORTED
+    assert l.seld_scalar_f32(None, 1, 7, 100, 64, 16, None, None, None, 1e-5, None) == _abi.SELD_EINVAL  # mean without var
+    assert l.seld_scalar_wav2img_f32(None, 0, 7, 1001, 64, 256, None, None, None, None, 0.0, None, None) == _abi.SELD_OK
+    assert l.seld_scalar_wav2img_f32(None, 1, 7, 1001, 64, 250, None, None, None, None, 0.0, None, None) == _abi.SELD_EINVAL
+    assert l.seld_scalar_wav2img_f32(None, 1, 7, 1001, 64, 256, None, None, None, None, 0.0, None, None) == _abi.SELD_EINVAL
+    assert l.seld_scalar_wav2img_f32(None, 1, 7, 1001, 6, 6, None, None, None, None, 0.0, None, None) == _abi.SELD_EUNSUPPORTED

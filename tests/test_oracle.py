@@ -1,11 +1,15 @@
 """CPU: pin the oracle (numpy restatement + torch port) to golden vectors made from the real
 reference (tests/golden/make_golden.py).  The reference ships no vectors of its own."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from conftest import assert_blocks_close, block_err, golden_input
 from oracle import seld_oracle as so
+from oracle import seld_oracle as oracle
+from oracle import synth
 from oracle import torch_port as tp
 from pseldnets_b200 import filterbank as fbk
 
@@ -99,3 +103,34 @@ def test_mic_oracle_self_consistency():
     assert int(np.argmax(y64[0, 4, 10])) == 32 + d
     assert int(np.argmax(y64[0, 5, 10])) == 32          # identical channels: lag 0
     assert y64[0, :4].min() >= y64[0, :4].max() - 80.0 - 1e-9
+
+
+def test_epilogue_oracle_matches_reference_goldens():
+    """scalar_eval / reshape_wav2img against the reference's own BatchNorm2d loop and
+    HTSAT_Swin_Transformer.reshape_wav2img (tests/golden/make_golden_epilogue.py): bit-exact."""
+    import hashlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'epilogue.npz'))
+    for name in ['pad', 'exact', 'crop', 'tiny', 'r1']:
+        seed, B, C, T, M, S = (int(v) for v in g[name + '/recipe'])
+        x = synth.feature_like(seed, B, C, T, M)
+        xs = oracle.scalar_eval(x, *synth.scalar_params(seed + 1000, C, M), 1e-5)
+        assert np.array_equal(oracle.reshape_wav2img(x, S), g[name + '/img']), name
+        assert np.array_equal(xs, g[name + '/scalar']), name
+        assert np.array_equal(oracle.reshape_wav2img(xs, S), g[name + '/scalar_img']), name
+    seed, B, C, T, M, S = (int(v) for v in g['full/recipe'])
+    x = synth.feature_like(seed, B, C, T, M)
+    img = oracle.reshape_wav2img(x, S)
+    assert img.shape == (B, C, S, S)
+    assert hashlib.sha256(img.tobytes()).digest() == g['full/img_sha256'].tobytes()
+    xs = oracle.scalar_eval(x, *synth.scalar_params(seed + 1000, C, M), 1e-5)
+    assert np.array_equal(xs[:, :, ::11, ::3], g['full/scalar_sub'])
+    assert np.array_equal(oracle.reshape_wav2img(xs, S)[:, :, ::7, ::5], g['full/scalar_img_sub'])
+
+
+def test_epilogue_oracle_fold_semantics():
+    x = np.arange(2 * 1 * 10 * 4, dtype=np.float32).reshape(2, 1, 10, 4)
+    img = oracle.reshape_wav2img(x, 8)                       # r = 2, target_T = 16: 6 frames of padding
+    assert img.shape == (2, 1, 8, 8)
+    assert img[1, 0, 2, 3] == x[1, 0, 3, 2]                  # piece 0: row m, column t
+    assert img[0, 0, 4 + 1, 1] == x[0, 0, 8 + 1, 1]          # piece 1 sits below piece 0
+    assert not img[:, :, 4:, 2:].any()                       # frames 10..15 are zero padding
