@@ -324,6 +324,82 @@ def run_epilogue(args):
         'gpu_launches': n_launch, 'clocks': clocks}))
 
 
+def run_augment(args):
+    """SURVEY 8f-4 (extra measurement, 1 GPU): Rotation + WavMix waveform work on the cfg2 batch
+    (64, 4, 240000), ours (one launch each, in place) against the reference's own torch expressions
+    (rotate.py:72 per clip, wavmix.py:50) on the same GPU.  Draws are fixed: p = 0.8 of the clips rotated,
+    the 32 even clips mixed with a permutation of themselves."""
+    import numpy as np
+    import torch
+    import pseldnets_b200.augment as aug
+    from pseldnets_b200 import _abi
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    B, C, L = args.batch, 4, SR * CLIP_S
+    g = torch.Generator(device=dev).manual_seed(1239)
+    x = 0.1 * torch.randn(B, C, L, device=dev, generator=g)
+    rng = np.random.default_rng(7)
+    table = list(aug.TRANS_48.values())
+    rot = [(table[rng.integers(6)], rng.choice([-1, 1], size=3)) if rng.random() < 0.8 else None for _ in range(B)]
+    codes = torch.tensor([aug.ROT_IDENTITY if r is None else aug.rotation_code(r[0], (r[1][1], r[1][2], r[1][0])) for r in rot],
+                         dtype=torch.int32, device=dev)
+    dst = np.arange(0, B, 2)
+    src = rng.permutation(dst)
+    lam = torch.from_numpy(rng.beta(0.5, 0.5, size=len(dst)).astype(np.float32)).to(dev)
+    dst_t, src_t = torch.from_numpy(dst).to(dev), torch.from_numpy(src).to(dev)
+
+    def ours(x):
+        aug.rotate_waveforms(x, codes)
+        aug.wavmix_waveforms(x, dst, src, lam)
+
+    def reference(x):
+        for n, r in enumerate(rot):                       # rotate.py:13-36, waveform part
+            if r is None:
+                continue
+            (s_x, s_y, s_z), (sx, sy, sz) = r
+            d = x[n]
+            x[n] = torch.stack((d[0], sy * d[s_x], sz * d[s_y], sx * d[s_z]), axis=0)
+        lx = lam.reshape(-1, 1, 1)
+        x[dst_t] = lx * x[dst_t] + (1. - lx) * x[src_t]   # wavmix.py:50
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn(x)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0 = _abi.lib().seld_launch_count()
+    sampler.mark()
+    ms = timed(ours, args.steps, warm)
+    n_launch = int(_abi.lib().seld_launch_count() - l0)
+    clocks = sampler.stop()
+    ms_ref = timed(reference, max(3, args.steps // 10), 3)
+    n_rot = sum(r is not None for r in rot)
+    algo = n_rot * 3 * L * 4 * 2 + len(dst) * C * L * 4 * 2     # rotated: 3 channels read + written; mixed (cycles): read + written once
+    peak, peak_src = measured_peaks()
+    print(json.dumps({
+        'metric': 'audio-seconds/sec (waveform augmentation: Rotation + WavMix)', 'value': B * CLIP_S / (ms * 1e-3), 'unit': UNIT,
+        'n_gpus': 1, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '8f-4: FOA Rotation (%d of %d clips) + WavMix (%d clips, cyclic) in place on the cfg2 batch (%d,4,240000); '
+                               'batch 246 MB > L2' % (n_rot, B, len(dst), B)},
+        'roofline': {'bound': 'hbm', 'achieved': algo / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                     'frac': algo / (ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_step': algo, 'kernel': 'seld::aug::foa_rotate_kernel + seld::aug::wavmix_kernel'},
+        'torch_expressions_same_gpu': {'ms_per_step': ms_ref, 'speedup': ms_ref / ms,
+                                       'what': 'rotate.py:72 per clip + wavmix.py:50 in torch eager'},
+        'gpu_launches': n_launch, 'clocks': clocks}))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -454,7 +530,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='clips per GPU per step (cfg2: 64)')
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'wav2img'],
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'wav2img', 'augment'],
                     help='cfg2 = BASELINE metric (default); cfg3 = MIC log-mel+GCC B=64; cfg4 = L3DAS22 dual-FOA '
                          '8 ch 32 kHz, global batch 128 sharded by clip (extra measurements, not the headline)')
     ap.add_argument('--cpu-seconds', type=float, default=10.0, help='bound on the cpu_baseline sample')
@@ -464,6 +540,8 @@ def main():
         run_reference(args)
     elif args.workload == 'wav2img':
         run_epilogue(args)
+    elif args.workload == 'augment':
+        run_augment(args)
     elif args.workload != 'cfg2':
         run_extra(args)
     else:

@@ -108,6 +108,43 @@ int seld_scalar_wav2img_f32(const float* x, int64_t B, int C, int64_t T, int M, 
                             const float* mean, const float* var, const float* weight, const float* bias,
                             float eps, float* img, void* stream);
 
+/* ---- Waveform-domain augmentation of the staged batch, the step before the extractors in
+ * the reference's training loop (src/models/model_module.py:53-58).  The random draws and the label
+ * bookkeeping stay with the caller; these entry points do the waveform arithmetic of a whole batch in
+ * one launch, in place, bit-identical to the reference's torch expressions.
+ *
+ * seld_foa_rotate_f32: Rotation.transform48 / transform16 (src/augment/rotate.py:47-99),
+ *   x[b] <- stack(x[b][0], sy * x[b][s_x], sz * x[b][s_y], sx * x[b][s_z])   for every rotated clip b.
+ * x (B, C >= 4, L) device fp32 with element strides (stride_b, stride_c, 1); codes (B,) device int32:
+ * SELD_ROT_CODE(source channel of output channels 1, 2, 3; their negate flags), or SELD_ROT_IDENTITY for
+ * a clip the draw left alone (no memory traffic).  Channel 0 and channels >= 4 are never touched. */
+#define SELD_ROT_CODE(s1, s2, s3, n1, n2, n3) \
+    ((int32_t)((s1) | ((s2) << 2) | ((s3) << 4) | ((n1) ? 0x100 : 0) | ((n2) ? 0x200 : 0) | ((n3) ? 0x400 : 0)))
+#define SELD_ROT_IDENTITY ((int32_t)-1)
+int seld_foa_rotate_f32(float* x, int64_t B, int C, int64_t L, int64_t stride_b, int64_t stride_c,
+                        const int32_t* codes, void* stream);
+
+/* seld_wavmix_f32: WavMix's waveform line (src/augment/wavmix.py:50),
+ *   x[dst_k] <- lam_k * x[dst_k] + (1 - lam_k) * x[src_k],  k < n_ops,
+ * every right-hand side taken before any assignment (the reference gathers first).  `ops` is a device
+ * array in the order seld_wavmix_order produced: the kernel walks it keeping the previous source in
+ * registers, which is what makes the in-place update safe when sources are also destinations.
+ *
+ * seld_wavmix_order: host-only helper (no CUDA call).  dst / src: n clip indices each in [0, B), no
+ * index repeated within dst nor within src (true for the reference: an index list and a permutation);
+ * lam: n mixing weights.  Writes n ops to ops_host, ordered along the chains dst_k -> src_k. */
+typedef struct seld_mix_op {
+    int32_t dst, src;
+    float lam;
+    int32_t flags;     /* SELD_MIX_* */
+} seld_mix_op;
+#define SELD_MIX_BEGIN 1      /* first op of a chain: load x[dst] (and remember it as the chain head) */
+#define SELD_MIX_USE_HEAD 2   /* the source is the chain head, already overwritten: use the remembered copy */
+int seld_wavmix_order(const int64_t* dst, const int64_t* src, const float* lam, int n, int64_t B,
+                      seld_mix_op* ops_host);
+int seld_wavmix_f32(float* x, int64_t B, int C, int64_t L, int64_t stride_b, int64_t stride_c,
+                    const seld_mix_op* ops, int n_ops, void* stream);
+
 /* Kernels enqueued by this library since load (all entry points, all plans). */
 uint64_t seld_launch_count(void);
 /* cudaError_t of the most recent failing runtime call on this thread (0 if none). */

@@ -42,6 +42,12 @@ SIGNATURES = {
     'seld_scalar_wav2img_f32': (ctypes.c_int, [ctypes.c_void_p, _i64, ctypes.c_int, _i64, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    'seld_foa_rotate_f32': (ctypes.c_int, [ctypes.c_void_p, _i64, ctypes.c_int, _i64, _i64, _i64, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
+    'seld_wavmix_order': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _i64,
+                                         ctypes.c_void_p]),
+    'seld_wavmix_f32': (ctypes.c_int, [ctypes.c_void_p, _i64, ctypes.c_int, _i64, _i64, _i64, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_void_p]),
     'seld_launch_count': (ctypes.c_uint64, []),
     'seld_last_cuda_error': (ctypes.c_int, []),
     'seld_strerror': (ctypes.c_char_p, [ctypes.c_int]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libseldfeat.so')
-SOURCES = ['seld_foa.cu', 'seld_foa_iv2.cu', 'seld_foa_iv3.cu', 'seld_mic.cu', 'seld_epilogue.cu', 'seld_abi.cu']
+SOURCES = ['seld_foa.cu', 'seld_foa_iv2.cu', 'seld_foa_iv3.cu', 'seld_mic.cu', 'seld_epilogue.cu', 'seld_augment.cu', 'seld_abi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -478,6 +478,70 @@ extern "C" int seld_scalar_wav2img_f32(const float* x, int64_t B, int C, int64_t
     return SELD_OK;
 }
 
+// ---- waveform-domain augmentation
+extern "C" int seld_foa_rotate_f32(float* x, int64_t B, int C, int64_t L, int64_t stride_b, int64_t stride_c,
+                                   const int32_t* codes, void* stream) {
+    if (B < 0 || C < 4 || L < 1) return SELD_EINVAL;                    // rotate.py indexes channels 0..3
+    if (B == 0) return SELD_OK;
+    if (!x || !codes) return SELD_EINVAL;
+    if ((uintptr_t)x & 3) return SELD_EINVAL;
+    cudaError_t e = seld::foa_rotate_launch(x, B, L, stride_b, stride_c, codes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
+extern "C" int seld_wavmix_order(const int64_t* dst, const int64_t* src, const float* lam, int n, int64_t B,
+                                 seld_mix_op* out) {
+    if (n < 0 || B < 0) return SELD_EINVAL;
+    if (n == 0) return SELD_OK;
+    if (!dst || !src || !lam || !out) return SELD_EINVAL;
+    std::vector<int> writer(B, -1), reader(B, -1);                      // op that writes / reads clip b
+    for (int k = 0; k < n; ++k) {
+        if (dst[k] < 0 || dst[k] >= B || src[k] < 0 || src[k] >= B) return SELD_EINVAL;
+        if (writer[dst[k]] >= 0 || reader[src[k]] >= 0) return SELD_EINVAL;   // repeated index
+        writer[dst[k]] = k; reader[src[k]] = k;
+    }
+    std::vector<char> done(n, 0);
+    int m = 0;
+    auto emit = [&](int k, int flags) {
+        out[m].dst = (int32_t)dst[k]; out[m].src = (int32_t)src[k]; out[m].lam = lam[k]; out[m].flags = flags;
+        done[k] = 1; ++m;
+    };
+    // open chains: start at a destination nobody reads, follow dst -> src while the source is itself mixed
+    for (int k0 = 0; k0 < n; ++k0) {
+        if (done[k0] || reader[dst[k0]] >= 0) continue;
+        int k = k0, flags = SELD_MIX_BEGIN;
+        while (k >= 0 && !done[k]) { emit(k, flags); flags = 0; k = writer[src[k]]; }
+    }
+    // what is left are closed cycles: the last op's source is the (overwritten) first destination
+    for (int k0 = 0; k0 < n; ++k0) {
+        if (done[k0]) continue;
+        int k = k0, flags = SELD_MIX_BEGIN;
+        while (!done[k]) {
+            const bool closes = src[k] == dst[k0];
+            emit(k, flags | (closes ? SELD_MIX_USE_HEAD : 0));
+            flags = 0;
+            if (closes) break;
+            k = writer[src[k]];
+        }
+    }
+    return m == n ? SELD_OK : SELD_EINVAL;
+}
+
+extern "C" int seld_wavmix_f32(float* x, int64_t B, int C, int64_t L, int64_t stride_b, int64_t stride_c,
+                               const seld_mix_op* ops, int n_ops, void* stream) {
+    if (B < 0 || C < 1 || L < 1 || n_ops < 0) return SELD_EINVAL;
+    if (B == 0 || n_ops == 0) return SELD_OK;
+    if (!x || !ops) return SELD_EINVAL;
+    if (((uintptr_t)x & 3) || ((uintptr_t)ops & 15)) return SELD_EINVAL;
+    if (C > 65535) return SELD_EUNSUPPORTED;
+    cudaError_t e = seld::wavmix_launch(x, C, L, stride_b, stride_c, ops, n_ops, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
 extern "C" uint64_t seld_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int seld_last_cuda_error(void) { return g_last_cuda; }
 

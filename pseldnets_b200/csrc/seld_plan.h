@@ -1,5 +1,6 @@
 // Internal (not exported) declarations shared by the kernels and the C-ABI layer.
 #pragma once
+#include "../../include/seldfeat.h"
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -79,5 +80,11 @@ struct ScalarArgs {
 cudaError_t scalar_launch(float* x, const ScalarArgs& s, int64_t B, int C, int T, int M, int sm_count, cudaStream_t st);
 cudaError_t scalar_wav2img_launch(const float* x, float* img, const ScalarArgs& s, int64_t B, int C, int T, int M, int S,
                                   int sm_count, cudaStream_t st);
+
+// waveform-domain augmentation (seld_augment.cu)
+cudaError_t foa_rotate_launch(float* x, int64_t B, int64_t L, int64_t stride_b, int64_t stride_c, const int32_t* codes,
+                              cudaStream_t st);
+cudaError_t wavmix_launch(float* x, int C, int64_t L, int64_t stride_b, int64_t stride_c, const struct seld_mix_op* ops,
+                          int n_ops, cudaStream_t st);
 
 }  // namespace seld

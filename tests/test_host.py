@@ -178,3 +178,52 @@ def test_epilogue_abi_argument_checks_without_gpu():
     assert l.seld_scalar_wav2img_f32(None, 1, 7, 1001, 64, 250, None, None, None, None, 0.0, None, None) == _abi.SELD_EINVAL
     assert l.seld_scalar_wav2img_f32(None, 1, 7, 1001, 64, 256, None, None, None, None, 0.0, None, None) == _abi.SELD_EINVAL
     assert l.seld_scalar_wav2img_f32(None, 1, 7, 1001, 6, 6, None, None, None, None, 0.0, None, None) == _abi.SELD_EUNSUPPORTED
+
+
+def test_wavmix_order_host_logic():
+    """seld_wavmix_order (host only): every pair is emitted once, and walking the list the way the kernel
+    does reproduces the gather-then-scatter semantics of wavmix.py:50 on a CPU model."""
+    import pseldnets_b200.augment as aug
+    rng = np.random.default_rng(0)
+    BEGIN, USE_HEAD = 1, 2
+    for trial in range(200):
+        B = int(rng.integers(1, 12))
+        n = int(rng.integers(0, B + 1))
+        dst = rng.permutation(B)[:n]
+        src = rng.permutation(B)[:n] if trial % 2 else rng.permutation(dst)
+        lam = rng.random(n).astype(np.float32)
+        ops = aug.wavmix_order(dst, src, lam, B)
+        assert sorted(zip(ops[:, 0], ops[:, 1])) == sorted(zip(dst, src))
+        x = rng.standard_normal(B).astype(np.float32)
+        want = x.copy()
+        want[dst] = lam * x[dst] + (np.float32(1) - lam) * x[src]
+        got, cur, head = x.copy(), None, None
+        for d, s, lbits, fl in ops:
+            l = np.array([lbits], np.int32).view(np.float32)[0]
+            if fl & BEGIN:
+                cur = head = got[d]
+            else:
+                assert d == prev_src                          # a chain continues at the previous source
+            nxt = head if fl & USE_HEAD else got[s]
+            got[d] = l * cur + (np.float32(1) - l) * nxt
+            cur, prev_src = nxt, s
+        assert np.array_equal(got, want), (dst, src, ops)
+    with pytest.raises(ValueError):
+        aug.wavmix_order([0, 0], [1, 2], [0.5, 0.5], 4)
+    with pytest.raises(ValueError):
+        aug.wavmix_order([0, 1], [2, 2], [0.5, 0.5], 4)
+    with pytest.raises(ValueError):
+        aug.wavmix_order([0], [4], [0.5], 4)
+    assert aug.rotation_code((1, 2, 3), (1, 1, 1)) == 1 | (2 << 2) | (3 << 4)
+    assert aug.rotation_code((3, 2, 1), (-1, 1, -1)) == (3 | (2 << 2) | (1 << 4) | 0x100 | 0x400)
+
+
+def test_augment_abi_argument_checks_without_gpu():
+    l = _abi.lib()
+    assert l.seld_foa_rotate_f32(None, 0, 4, 100, 400, 100, None, None) == _abi.SELD_OK
+    assert l.seld_foa_rotate_f32(None, 2, 3, 100, 300, 100, None, None) == _abi.SELD_EINVAL     # needs channels 0..3
+    assert l.seld_foa_rotate_f32(None, 2, 4, 100, 400, 100, None, None) == _abi.SELD_EINVAL     # null pointers
+    assert l.seld_wavmix_f32(None, 2, 4, 100, 400, 100, None, 0, None) == _abi.SELD_OK
+    assert l.seld_wavmix_f32(None, 2, 4, 100, 400, 100, None, 1, None) == _abi.SELD_EINVAL
+    assert l.seld_wavmix_order(None, None, None, 0, 4, None) == _abi.SELD_OK
+    assert l.seld_wavmix_order(None, None, None, 1, 4, None) == _abi.SELD_EINVAL
