@@ -59,7 +59,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     constexpr int W = kW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // lane-major tables read with 128-bit loads (row stride = 4 mod 32 words: conflict-free)
-    float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: (cos, -sin) of W1024^(lane*brev5(p)), p = 0..31
+    float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: W1024^(lane*brev5(p)) as (cos_p, cos_p+1, -sin_p, -sin_p+1), p even
     float* win_s = tw_s + 32 * kTwStride;                                  // [lane][kWinStride]: window[32*m + lane] * 0.5
     float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride
     int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
@@ -68,8 +68,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
-        const float2 w = pd.tw[brev5(r) * 32 + l];
-        tw_s[l * kTwStride + 2 * r] = w.x; tw_s[l * kTwStride + 2 * r + 1] = w.y;
+        const float2 w = pd.tw[brev5(r) * 32 + l];                         // positions (2j, 2j+1) share one float4: (cos, cos', -sin, -sin')
+        tw_s[l * kTwStride + 4 * (r >> 1) + (r & 1)] = w.x; tw_s[l * kTwStride + 4 * (r >> 1) + 2 + (r & 1)] = w.y;
         win_s[l * kWinStride + r] = pd.win[i];
     }
     for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
@@ -161,12 +161,12 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
             if constexpr (p2 > 0) {
                 const float2 r = re[2 * p2], i = im[2 * p2];
-                re[2 * p2] = vfmas(i, -w4.y, vmuls(r, w4.x));
-                im[2 * p2] = vfmas(i, w4.x, vmuls(r, w4.y));
+                re[2 * p2] = vfmas(i, -w4.z, vmuls(r, w4.x));
+                im[2 * p2] = vfmas(i, w4.x, vmuls(r, w4.z));
             }
             const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
-            re[2 * p2 + 1] = vfmas(i, -w4.w, vmuls(r, w4.z));
-            im[2 * p2 + 1] = vfmas(i, w4.z, vmuls(r, w4.w));
+            re[2 * p2 + 1] = vfmas(i, -w4.w, vmuls(r, w4.y));
+            im[2 * p2 + 1] = vfmas(i, w4.y, vmuls(r, w4.w));
         });
         static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = re[p]; });
         __syncwarp();
@@ -263,26 +263,26 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             __syncwarp();                                                   // rows become the exchange buffer again
         }
 
-        // ---------------- GCC-PHAT: pass 0 = pairs (01,02 | 03,12), pass 1 = pairs (13,23 | -, -)
-        auto gcc_pass = [&](auto pass_c) {
-            constexpr int pass = decltype(pass_c)::value;
-            // Z1 = ph(a1) + i ph(b1) in .x halves, Z2 = ph(a2) + i ph(b2) in .y halves
+        // ---------------- GCC-PHAT.  Two real correlations per complex inverse transform (Z = ph_a + i ph_b):
+        // pass 0 = pairs (01, 02 | 03, 12) as two transforms packed in float2 halves, pass 1 = pairs (13, 23) as
+        // one transform packed internally (fft32_dit).
+        constexpr float kInvN = 1.0f / 1024.0f;
+        // unit phasor of channel c at bin k = lane + 32 m (bins above 512 are conj(u[1024 - k]))
+        auto load_u = [&](int c, int kk, float sg) {
+            float2 u = spec[c * kSpecStride + kk];
+            u.y *= sg;
+            return u;
+        };
+        {
             static_for<0, 32>([&](auto mi) {
                 constexpr int m = decltype(mi)::value;
                 const int k = lane + 32 * m;
                 const bool up = k > 512;
                 const int kk = up ? 1024 - k : k;
-                const float sg = up ? -1.0f : 1.0f;                       // bins above 512: conj(u[1024-k])
-                float2 a1, b1, a2, b2;
-                float2 u1 = spec[1 * kSpecStride + kk], u2 = spec[2 * kSpecStride + kk], u3 = spec[3 * kSpecStride + kk];
-                u1.y *= sg; u2.y *= sg; u3.y *= sg;
-                if constexpr (pass == 0) {
-                    float2 u0 = spec[0 * kSpecStride + kk];
-                    u0.y *= sg;
-                    a1 = cross_phasor(u0, u1); b1 = cross_phasor(u0, u2); a2 = cross_phasor(u0, u3); b2 = cross_phasor(u1, u2);
-                } else {
-                    a1 = cross_phasor(u1, u3); b1 = cross_phasor(u2, u3); a2 = make_float2(0.f, 0.f); b2 = a2;
-                }
+                const float sg = up ? -1.0f : 1.0f;
+                const float2 u0 = load_u(0, kk, sg), u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
+                const float2 a1 = cross_phasor(u0, u1), b1 = cross_phasor(u0, u2);
+                const float2 a2 = cross_phasor(u0, u3), b2 = cross_phasor(u1, u2);
                 re[m] = make_float2(a1.x - b1.y, a2.x - b2.y);
                 im[m] = make_float2(a1.y + b1.x, a2.y + b2.x);
             });
@@ -293,12 +293,12 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
                 if constexpr (p2 > 0) {
                     const float2 r = re[2 * p2], i = im[2 * p2];
-                    re[2 * p2] = vfmas(i, w4.y, vmuls(r, w4.x));
-                    im[2 * p2] = vfmas(i, w4.x, vmuls(r, -w4.y));
+                    re[2 * p2] = vfmas(i, w4.z, vmuls(r, w4.x));
+                    im[2 * p2] = vfmas(i, w4.x, vmuls(r, -w4.z));
                 }
                 const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
-                re[2 * p2 + 1] = vfmas(i, w4.w, vmuls(r, w4.z));
-                im[2 * p2 + 1] = vfmas(i, w4.z, vmuls(r, -w4.w));
+                re[2 * p2 + 1] = vfmas(i, w4.w, vmuls(r, w4.y));
+                im[2 * p2 + 1] = vfmas(i, w4.y, vmuls(r, -w4.w));
             });
             static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = re[p]; });
             __syncwarp();
@@ -322,23 +322,77 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             static_for<1, 32>([&](auto ki) {
                 constexpr int k1 = decltype(ki)::value;
                 constexpr float c = (float)(k1 <= 16 ? cos32(k1) : cos32(32 - k1));
-                constexpr float s = (float)(k1 <= 16 ? sin32(k1) : -sin32(32 - k1));
+                constexpr float sn = (float)(k1 <= 16 ? sin32(k1) : -sin32(32 - k1));
                 c0r = vadd(c0r, re[k1]); c0i = vadd(c0i, im[k1]);
-                c31r = vfmas(im[k1], s, vfmas(re[k1], c, c31r));            // Re += r c + i s
-                c31i = vfmas(re[k1], -s, vfmas(im[k1], c, c31i));           // Im += i c - r s
+                c31r = vfmas(im[k1], sn, vfmas(re[k1], c, c31r));           // Re += r c + i s
+                c31i = vfmas(re[k1], -sn, vfmas(im[k1], c, c31i));          // Im += i c - r s
             });
-            constexpr float kInvN = 1.0f / 1024.0f;
-            // real part = first pair of the job, imaginary part = second pair
-            float* g = ob + (int64_t)(4 + 4 * pass) * ch_stride;
+            // real part = first pair of a transform, imaginary part = second pair
+            float* g = ob + (int64_t)4 * ch_stride;
             g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;
             g[1 * ch_stride + lane] = c31i.x * kInvN;  g[1 * ch_stride + 32 + lane] = c0i.x * kInvN;
-            if constexpr (pass == 0) {
-                g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;
-                g[3 * ch_stride + lane] = c31i.y * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.y * kInvN;
-            }
-        };
-        gcc_pass(std::integral_constant<int, 0>{});
-        gcc_pass(std::integral_constant<int, 1>{});
+            g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;
+            g[3 * ch_stride + lane] = c31i.y * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.y * kInvN;
+        }
+        {
+            // one transform: position p of (zr, zi) holds the input pair (z[m = 2p], z[m = 2p + 1])
+            float2 zr[16], zi[16];
+            static_for<0, 16>([&](auto pi) {
+                constexpr int p = decltype(pi)::value;
+                float rr[2], ii[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = lane + 32 * (2 * p + e);
+                    const bool up = k > 512;
+                    const int kk = up ? 1024 - k : k;
+                    const float sg = up ? -1.0f : 1.0f;
+                    const float2 u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
+                    const float2 a = cross_phasor(u1, u3), b = cross_phasor(u2, u3);
+                    rr[e] = a.x - b.y; ii[e] = a.y + b.x;
+                }
+                zr[p] = make_float2(rr[0], rr[1]); zi[p] = make_float2(ii[0], ii[1]);
+            });
+            fft32_dit(zi, zr);                                              // position q': (A[lane][q], A[lane][q + 16]), q = brev4(q')
+            float* fr = R;                                                  // two planes of 32 x 34 floats in the exchange area
+            float* fi = R + 32 * kXStride;
+            static_for<0, 16>([&](auto qi) {
+                constexpr int qp = decltype(qi)::value;
+                constexpr int q = brev4(qp);
+                // table positions brev5(q) (even) and brev5(q + 16) = brev5(q) + 1 share one float4: (cos, cos', -sin, -sin')
+                const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 2 * brev5(q));
+                float2 r = zr[qp], i = zi[qp];
+                if constexpr (q == 0) {                                     // W^0 = 1 for n2 = 0; n2 = 16 still needs its factor
+                    const float r1 = r.y, i1 = i.y;
+                    r.y = fmaf(i1, w4.w, r1 * w4.y);
+                    i.y = fmaf(i1, w4.y, r1 * -w4.w);
+                } else {
+                    const float2 C2 = make_float2(w4.x, w4.y), S2 = make_float2(w4.z, w4.w);
+                    const float2 t = __fmul2_rn(make_float2(-r.x, -r.y), S2);
+                    r = __ffma2_rn(i, S2, __fmul2_rn(r, C2));
+                    i = __ffma2_rn(i, C2, t);
+                }
+                fr[q * kXStride + lane] = r.x; fr[(q + 16) * kXStride + lane] = r.y;
+                fi[q * kXStride + lane] = i.x; fi[(q + 16) * kXStride + lane] = i.y;
+            });
+            __syncwarp();
+            // second stage for n1 = 0 and 31, two k1 terms per packed operation
+            float2 a0r = make_float2(0.f, 0.f), a0i = a0r, a31r = a0r, a31i = a0r;
+            static_for<0, 16>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const float2 pr = *reinterpret_cast<const float2*>(fr + lane * kXStride + 2 * j);   // (A'[2j], A'[2j + 1])
+                const float2 pi = *reinterpret_cast<const float2*>(fi + lane * kXStride + 2 * j);
+                constexpr int k0 = 2 * j, k1 = 2 * j + 1;
+                constexpr float c0 = (float)(k0 <= 16 ? cos32(k0) : cos32(32 - k0)), c1 = (float)(k1 <= 16 ? cos32(k1) : cos32(32 - k1));
+                constexpr float s0 = (float)(k0 <= 16 ? sin32(k0) : -sin32(32 - k0)), s1 = (float)(k1 <= 16 ? sin32(k1) : -sin32(32 - k1));
+                a0r = __fadd2_rn(a0r, pr); a0i = __fadd2_rn(a0i, pi);
+                a31r = __ffma2_rn(pi, make_float2(s0, s1), __ffma2_rn(pr, make_float2(c0, c1), a31r));
+                a31i = __ffma2_rn(pr, make_float2(-s0, -s1), __ffma2_rn(pi, make_float2(c0, c1), a31i));
+            });
+            __syncwarp();                                                   // the next frame reuses the exchange area
+            float* g = ob + (int64_t)8 * ch_stride;
+            g[0 * ch_stride + lane] = (a31r.x + a31r.y) * kInvN;  g[0 * ch_stride + 32 + lane] = (a0r.x + a0r.y) * kInvN;
+            g[1 * ch_stride + lane] = (a31i.x + a31i.y) * kInvN;  g[1 * ch_stride + 32 + lane] = (a0i.x + a0i.y) * kInvN;
+        }
     }
     flush_max();
 }
