@@ -45,10 +45,14 @@ __device__ __forceinline__ int f2key(float f) { const int b = __float_as_int(f);
 __device__ __forceinline__ float inv_mag(float p) { return p > 1e-37f ? rsqrt_ftz(p) : 0.0f; }
 
 // conj(ua) * ub for unit (or zero) phasors; a vanishing product means angle(0) = 0 -> phasor 1
+// kCheck = false: the caller knows that no channel of this frame has a vanishing bin, so no product vanishes
+template <bool kCheck>
 __device__ __forceinline__ float2 cross_phasor(float2 ua, float2 ub) {
     float re = fmaf(ua.y, ub.y, ua.x * ub.x);
     const float im = fmaf(-ua.y, ub.x, ua.x * ub.y);
-    if (re == 0.0f && im == 0.0f) re = 1.0f;
+    if constexpr (kCheck) {
+        if (re == 0.0f && im == 0.0f) re = 1.0f;
+    }
     return make_float2(re, im);
 }
 }  // namespace mic
@@ -187,6 +191,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         fft32(re, im);
 
         // ---------------- untangle: spectra -> spec[c][k], powers -> rows
+        float min_n = 1.0f;                                                 // becomes 0 if any channel has a vanishing bin
         static_for<0, 17>([&](auto kbi) {
             constexpr int kb = decltype(kbi)::value;
             constexpr int p = brev5(kb & 31);
@@ -209,11 +214,14 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             if (kb < 16 || lane == 0) {
                 const int k = lane + 32 * kb;
                 // PHAT only needs phases: keep X_c / |X_c| (unit phasors) for the GCC passes
-                const float n0 = inv_mag(p02.x), n1 = inv_mag(p13.x), n2 = inv_mag(p02.y), n3 = inv_mag(p13.y);
-                spec[0 * kSpecStride + k] = make_float2(ar.x * n0, ai.x * n0);
-                spec[1 * kSpecStride + k] = make_float2(br.x * n1, bi.x * n1);
-                spec[2 * kSpecStride + k] = make_float2(ar.y * n2, ai.y * n2);
-                spec[3 * kSpecStride + k] = make_float2(br.y * n3, bi.y * n3);
+                const float2 n02 = make_float2(inv_mag(p02.x), inv_mag(p02.y)), n13 = make_float2(inv_mag(p13.x), inv_mag(p13.y));
+                min_n = fminf(min_n, fminf(fminf(n02.x, n02.y), fminf(n13.x, n13.y)));
+                const float2 ur02 = __fmul2_rn(ar, n02), ui02 = __fmul2_rn(ai, n02);
+                const float2 ur13 = __fmul2_rn(br, n13), ui13 = __fmul2_rn(bi, n13);
+                spec[0 * kSpecStride + k] = make_float2(ur02.x, ui02.x);
+                spec[1 * kSpecStride + k] = make_float2(ur13.x, ui13.x);
+                spec[2 * kSpecStride + k] = make_float2(ur02.y, ui02.y);
+                spec[3 * kSpecStride + k] = make_float2(ur13.y, ui13.y);
                 float* q = R + 32 * kb + wofs[kb & 3];
                 q[0 * kRowWords] = p02.x;
                 q[1 * kRowWords] = p13.x;
@@ -273,19 +281,26 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             u.y *= sg;
             return u;
         };
+        // angle(0) = 0: a vanishing cross-spectrum bin must contribute the phasor 1.  That needs two compares and a
+        // select per product; frames without any vanishing bin (all but digital silence / dead channels) skip them.
+        const bool any_zero = __any_sync(0xffffffffu, min_n == 0.0f);
         {
-            static_for<0, 32>([&](auto mi) {
-                constexpr int m = decltype(mi)::value;
-                const int k = lane + 32 * m;
-                const bool up = k > 512;
-                const int kk = up ? 1024 - k : k;
-                const float sg = up ? -1.0f : 1.0f;
-                const float2 u0 = load_u(0, kk, sg), u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
-                const float2 a1 = cross_phasor(u0, u1), b1 = cross_phasor(u0, u2);
-                const float2 a2 = cross_phasor(u0, u3), b2 = cross_phasor(u1, u2);
-                re[m] = make_float2(a1.x - b1.y, a2.x - b2.y);
-                im[m] = make_float2(a1.y + b1.x, a2.y + b2.x);
-            });
+            auto build = [&](auto check_c) {
+                constexpr bool kCheck = decltype(check_c)::value;
+                static_for<0, 32>([&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    const int k = lane + 32 * m;
+                    const bool up = k > 512;
+                    const int kk = up ? 1024 - k : k;
+                    const float sg = up ? -1.0f : 1.0f;
+                    const float2 u0 = load_u(0, kk, sg), u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
+                    const float2 a1 = cross_phasor<kCheck>(u0, u1), b1 = cross_phasor<kCheck>(u0, u2);
+                    const float2 a2 = cross_phasor<kCheck>(u0, u3), b2 = cross_phasor<kCheck>(u1, u2);
+                    re[m] = make_float2(a1.x - b1.y, a2.x - b2.y);
+                    im[m] = make_float2(a1.y + b1.x, a2.y + b2.x);
+                });
+            };
+            if (any_zero) build(std::true_type{}); else build(std::false_type{});
             // inverse 32-point stage over m: swap(FFT(swap(z)))
             fft32(im, re);                                                  // position p: A[lane][n2 = brev5(p)]
             static_for<0, 16>([&](auto pi) {                                // table holds (cos, -sin): multiply by (cos + i sin)
@@ -337,21 +352,25 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         {
             // one transform: position p of (zr, zi) holds the input pair (z[m = 2p], z[m = 2p + 1])
             float2 zr[16], zi[16];
-            static_for<0, 16>([&](auto pi) {
-                constexpr int p = decltype(pi)::value;
-                float rr[2], ii[2];
+            auto build = [&](auto check_c) {
+                constexpr bool kCheck = decltype(check_c)::value;
+                static_for<0, 16>([&](auto pi) {
+                    constexpr int p = decltype(pi)::value;
+                    float rr[2], ii[2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int k = lane + 32 * (2 * p + e);
-                    const bool up = k > 512;
-                    const int kk = up ? 1024 - k : k;
-                    const float sg = up ? -1.0f : 1.0f;
-                    const float2 u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
-                    const float2 a = cross_phasor(u1, u3), b = cross_phasor(u2, u3);
-                    rr[e] = a.x - b.y; ii[e] = a.y + b.x;
-                }
-                zr[p] = make_float2(rr[0], rr[1]); zi[p] = make_float2(ii[0], ii[1]);
-            });
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = lane + 32 * (2 * p + e);
+                        const bool up = k > 512;
+                        const int kk = up ? 1024 - k : k;
+                        const float sg = up ? -1.0f : 1.0f;
+                        const float2 u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
+                        const float2 a = cross_phasor<kCheck>(u1, u3), b = cross_phasor<kCheck>(u2, u3);
+                        rr[e] = a.x - b.y; ii[e] = a.y + b.x;
+                    }
+                    zr[p] = make_float2(rr[0], rr[1]); zi[p] = make_float2(ii[0], ii[1]);
+                });
+            };
+            if (any_zero) build(std::true_type{}); else build(std::false_type{});
             fft32_dit(zi, zr);                                              // position q': (A[lane][q], A[lane][q + 16]), q = brev4(q')
             float* fr = R;                                                  // two planes of 32 x 34 floats in the exchange area
             float* fi = R + 32 * kXStride;

@@ -96,6 +96,23 @@ def test_mic_silence_and_errors():
     assert ext(torch.zeros(2, 4, 100, device='cuda')).shape == (2, 10, 0, 64)
 
 
+def test_mic_dead_channel_and_silent_tail():
+    """Vanishing cross-spectrum bins (angle(0) = 0 -> phasor 1) next to ordinary ones: one microphone
+    digitally silent, and a clip whose second half is zero fill (frames with and without vanishing bins
+    in the same launch)."""
+    from oracle import synth
+    ext = _mic()
+    x = synth.white(41, 2, 4, 4800)
+    x[0, 2] = 0.0                                            # dead microphone in clip 0
+    x[1, :, 2400:] = 0.0                                     # clip 1: silent tail
+    y = ext(torch.from_numpy(x).cuda()).cpu().numpy()
+    _check(y, _oracle(ext, x), 'dead channel / silent tail')
+    # pairs with the dead microphone: (0,2) (1,2) (2,3) = GCC planes 1, 3, 5 -> a delta at lag 0
+    for plane in (1, 3, 5):
+        g = y[0, 4 + plane]
+        assert np.abs(g[:, 32] - 1.0).max() < 1e-5 and np.abs(np.delete(g, 32, axis=1)).max() < 1e-5
+
+
 def test_mic_numpy_front():
     from oracle import synth
     cfg = make_cfg(24000, 240, 'hann', 'logmelgcc')
