@@ -93,20 +93,22 @@ scalar_kernel(float* __restrict__ x, const ScalarArgs s, int C, int T, int M, in
 // hit 8 different bank groups.
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 scalar_wav2img_kernel(const float* __restrict__ x, float* __restrict__ img, const ScalarArgs s,
-                      int C, int T, int M, int S, int R, int tiles_t, int tiles_m, int64_t n_tiles) {
+                      int B, int C, int T, int M, int S, int R, int tiles_t, int tiles_m, uint32_t n_tiles) {
     __shared__ __align__(16) float tile[kTile * kTile];
     const int tid = threadIdx.x;
     const int m4 = tid & 15, tq = tid >> 4;
     const int T_in = min(T, R * S);                                   // frames that survive the pad / crop
     int cur_c = -1, cur_mt = -1;
     Affine f;
-    for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
-        int64_t q = tl;
-        const int mt = (int)(q % tiles_m); q /= tiles_m;
-        const int tt = (int)(q % tiles_t); q /= tiles_t;
-        const int k = (int)(q % R); q /= R;
-        const int64_t plane = q;                                      // b * C + c
-        const int c = (int)(plane % C);
+    // strided walk: all resident blocks sweep the map together (measured: a contiguous run of tiles per block, or a
+    // channel-slowest order that would save recomputing the affine terms, both cost 5-8 % in DRAM locality)
+    for (uint32_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {  // 32-bit tile arithmetic: the decode is on every tile's path
+        uint32_t q = tl;
+        const int mt = (int)(q % (uint32_t)tiles_m); q /= (uint32_t)tiles_m;
+        const int tt = (int)(q % (uint32_t)tiles_t); q /= (uint32_t)tiles_t;
+        const int k = (int)(q % (uint32_t)R); q /= (uint32_t)R;
+        const uint32_t plane = q;                                     // b * C + c
+        const int c = (int)(plane % (uint32_t)C);
         const int m = mt * kTile + 4 * m4;                            // first of this thread's 4 mel bins
         const bool m_ok = m < M;
         if (c != cur_c || mt != cur_mt) {
@@ -170,6 +172,7 @@ cudaError_t scalar_wav2img_launch(const float* x, float* img, const ScalarArgs& 
     const int R = S / M;
     const int tiles_t = (S + kTile - 1) / kTile, tiles_m = (M + kTile - 1) / kTile;
     const int64_t n_tiles = B * C * R * tiles_t * tiles_m;
+    if (n_tiles > INT32_MAX) return cudaErrorInvalidConfiguration;
     static int per_sm = 0;                                            // resident blocks per SM (persistent grid)
     if (per_sm == 0) {
         int n = 0;
@@ -179,7 +182,7 @@ cudaError_t scalar_wav2img_launch(const float* x, float* img, const ScalarArgs& 
     }
     const int64_t resident = (int64_t)per_sm * sm_count;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
-    scalar_wav2img_kernel<<<grid, kThreads, 0, st>>>(x, img, s, C, T, M, S, R, tiles_t, tiles_m, n_tiles);
+    scalar_wav2img_kernel<<<grid, kThreads, 0, st>>>(x, img, s, (int)B, C, T, M, S, R, tiles_t, tiles_m, (uint32_t)n_tiles);
     return cudaGetLastError();
 }
 
