@@ -86,3 +86,23 @@ def lib():
 def check(code, where):
     if code != SELD_OK:
         raise SeldError(code, where)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """Context that makes `device` current for the launch -- free when it already is (the one-process-per-GPU case)."""
+    import torch
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)

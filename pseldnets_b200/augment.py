@@ -72,7 +72,7 @@ def rotate_waveforms(batch_x, codes):
     if B == 0 or L == 0:
         return batch_x
     codes = codes.to(device=batch_x.device, dtype=torch.int32, non_blocking=True).contiguous()
-    with torch.cuda.device(batch_x.device):
+    with _abi.device_guard(batch_x.device):
         rc = _abi.lib().seld_foa_rotate_f32(batch_x.data_ptr(), B, C, L, batch_x.stride(0), batch_x.stride(1),
                                             codes.data_ptr(), torch.cuda.current_stream(batch_x.device).cuda_stream)
     _abi.check(rc, 'seld_foa_rotate_f32')
@@ -111,7 +111,7 @@ def wavmix_waveforms(batch_x, dst, src, lambs):
     if len(ops) == 0 or L == 0:
         return batch_x
     ops_dev = torch.from_numpy(ops).to(batch_x.device, non_blocking=True)
-    with torch.cuda.device(batch_x.device):
+    with _abi.device_guard(batch_x.device):
         rc = _abi.lib().seld_wavmix_f32(batch_x.data_ptr(), B, C, L, batch_x.stride(0), batch_x.stride(1),
                                         ops_dev.data_ptr(), len(ops),
                                         torch.cuda.current_stream(batch_x.device).cuda_stream)

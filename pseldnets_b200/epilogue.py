@@ -95,7 +95,7 @@ def apply_scalar(x, scalar):
     if sp is None or x.numel() == 0:
         return x
     B, C, T, M = x.shape
-    with torch.cuda.device(x.device):
+    with _abi.device_guard(x.device):
         rc = _abi.lib().seld_scalar_f32(x.data_ptr(), B, C, T, M, *sp.pointers(), sp.eps,
                                         torch.cuda.current_stream(x.device).cuda_stream)
     _abi.check(rc, 'seld_scalar_f32')
@@ -117,7 +117,7 @@ def scalar_wav2img(x, scalar, spec_size=256):
     if B == 0:
         return img
     ptrs = sp.pointers() if sp is not None else (0, 0, 0, 0)
-    with torch.cuda.device(x.device):
+    with _abi.device_guard(x.device):
         rc = _abi.lib().seld_scalar_wav2img_f32(x.data_ptr(), B, C, T, M, spec_size, *ptrs,
                                                 sp.eps if sp is not None else 0.0, img.data_ptr(),
                                                 torch.cuda.current_stream(x.device).cuda_stream)

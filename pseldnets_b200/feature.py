@@ -117,7 +117,8 @@ class _ExtractorBase(nn.Module):
         out = torch.empty((B, C + self._extra_ch, T, self.n_mels), dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         fn = getattr(_abi.lib(), entry)
-        code = fn(plan.handle, x.data_ptr(), B, C, L, x.stride(0), x.stride(1), out.data_ptr(), stream)
+        with _abi.device_guard(x.device):
+            code = fn(plan.handle, x.data_ptr(), B, C, L, x.stride(0), x.stride(1), out.data_ptr(), stream)
         _abi.check(code, entry)
         return out
 
