@@ -11,11 +11,13 @@
 //   2. untangle -> the four spectra go to shared memory (4 x 513 complex), powers to 4 swizzled rows;
 //   3. segment-walk mel of the 4 power rows -> dB, stored unclamped; the running per-(clip, mic)
 //      maximum is kept in registers and flushed with one atomicMax per clip change;
-//   4. GCC-PHAT: two passes of two packed inverse transforms.  A transform's input is
+//   4. GCC-PHAT: three complex inverse transforms for the six pairs.  A transform's input is
 //      Z = ph_a + i*ph_b for two mic pairs (its real/imag outputs are the two correlations); lane l
 //      builds Z[l + 32m] for all m from the shared unit phasors X_c/|X_c| (bins above 512 are the
 //      conjugates of 1024-k), runs the 32-point inverse stage in registers, twiddles, exchanges, and -- because
 //      only lags [-32, 32) are kept -- evaluates just the two needed outputs of the second stage.
+//      Pass 0 does two transforms in the two float2 halves; pass 1 the third as one internally packed
+//      transform (fft32_dit) with scalar exchange planes.
 // A second, element-wise kernel applies the top_db floor once every frame's maximum is known.
 #include <cuda_runtime.h>
 #include <stdint.h>
