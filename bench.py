@@ -175,7 +175,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps * sample_b * CLIP_S / dt
     sample = '%d of 64 clips per step (10 s, 4 ch, 24 kHz), torch CPU fp32' % sample_b
-    print(json.dumps({
+    emit_json(({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -241,7 +241,7 @@ def run_extra(args):
         peak, peak_src = measured_peaks()
         n_global = nb * world if args.workload == 'cfg3' else 128
         algo = nb * (Cin * Lw * 4 + out_bytes)
-        print(json.dumps({'metric': 'audio-seconds/sec (%s)' % args.workload, 'value': n_global * CLIP_S / (ms * 1e-3), 'unit': UNIT,
+        emit_json(({'metric': 'audio-seconds/sec (%s)' % args.workload, 'value': n_global * CLIP_S / (ms * 1e-3), 'unit': UNIT,
                           'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
                           'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                           'config': {'workload': name},
@@ -308,7 +308,7 @@ def run_epilogue(args):
     peak, peak_src = measured_peaks()
     in_b, out_b = B * C * T * M * 4, B * C * S * S * 4
     algo = in_b + out_b
-    print(json.dumps({
+    emit_json(({
         'metric': 'audio-seconds/sec (backbone-input stage: scalar + reshape_wav2img)', 'value': B * CLIP_S / (ms_fused * 1e-3),
         'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_fused, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -386,7 +386,7 @@ def run_augment(args):
     n_rot = sum(r is not None for r in rot)
     algo = n_rot * 3 * L * 4 * 2 + len(dst) * C * L * 4 * 2     # rotated: 3 channels read + written; mixed (cycles): read + written once
     peak, peak_src = measured_peaks()
-    print(json.dumps({
+    emit_json(({
         'metric': 'audio-seconds/sec (waveform augmentation: Rotation + WavMix)', 'value': B * CLIP_S / (ms * 1e-3), 'unit': UNIT,
         'n_gpus': 1, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -518,12 +518,34 @@ def run_ours(args):
                     'path': 'pinned host -> LogmelIV_Extractor.forward_host (seld_logmel_iv_f32_host: %d-clip chunks, H2D / kernel / D2H on 3 streams) -> pinned host' % args.e2e_chunk},
             'gpu_launches': int(launches), 'clocks': clocks, 'outputs_finite': finite,
         }
-        print(json.dumps(out))
+        emit_json((out))
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries below us may print there too (NCCL's version banner does
+    on some hosts), so the real stdout is set aside for the JSON line and file descriptor 1 is pointed at stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=400)
