@@ -499,6 +499,27 @@ def run_ours(args):
             pass
         cpu_threads = os.cpu_count() or 1
         cpu_val, cpu_calls, cpu_secs = cpu_port_throughput(8, args.cpu_seconds, 200, cpu_threads)
+        library = None
+        if world == 1 and args.cpu_seconds > 0:
+            # the reference's op sequence (torch.stft -> |X|^2 -> matmul -> log10, IV arithmetic: cuFFT, cuBLAS
+            # and ~45 ATen launches) on the SAME GPU and batch -- the library baseline the fused kernel replaces
+            from oracle import torch_port
+            win_d, fb_d = ext.stft_extractor.window, ext.mel_scale.fb
+            for _ in range(2):
+                y_lib = torch_port.logmel_iv(x, win_d, fb_d, NFFT, HOP)
+            torch.cuda.synchronize()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for _ in range(5):
+                y_lib = torch_port.logmel_iv(x, win_d, fb_d, NFFT, HOP)
+            l1.record()
+            torch.cuda.synchronize()
+            lib_ms = l0.elapsed_time(l1) / 5
+            library = {'ms_per_step': lib_ms, 'value': audio_s / (lib_ms * 1e-3), 'unit': UNIT,
+                       'speedup_of_value': lib_ms / (total_ms / args.steps),
+                       'max_abs_diff_vs_ours': float((y_lib - y).abs().max()),
+                       'what': 'feature.py op sequence in torch eager on the same B200 (cuFFT / cuBLAS / ATen), same resident batch'}
+            del y_lib
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
@@ -518,6 +539,8 @@ def run_ours(args):
                     'path': 'pinned host -> LogmelIV_Extractor.forward_host (seld_logmel_iv_f32_host: %d-clip chunks, H2D / kernel / D2H on 3 streams) -> pinned host' % args.e2e_chunk},
             'gpu_launches': int(launches), 'clocks': clocks, 'outputs_finite': finite,
         }
+        if library is not None:
+            out['library_baseline_same_gpu'] = library
         emit_json((out))
     if world > 1:
         dist.destroy_process_group()
