@@ -253,6 +253,84 @@ def run_extra(args):
         dist.destroy_process_group()
 
 
+def run_epoch(args):
+    """cfg5 of BASELINE.json / SURVEY 8d: one epoch sweep of the reference's training set -- 67,000 one-minute clips
+    = 402,000 ten-second chunks (configs/data/default.yaml:15-21; chunked before extraction, preprocess.py:464-521)
+    -- sharded by chunk over the ranks, batches of 64 from a resident pool of 4 synthetic batches per rank (984 MB,
+    cycled; generation excluded from the time).  Time = max over ranks for the whole sweep."""
+    import torch
+    import torch.distributed as dist
+    import pseldnets_b200 as pb
+    from pseldnets_b200 import _abi, shard
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=dev)
+    n_chunks = 402000
+    lo, hi = shard.clip_shard(n_chunks, rank, world)
+    B = args.batch
+    n_local = hi - lo
+    steps = (n_local + B - 1) // B
+    ext = pb.get_afextractor(CFG).to(dev)
+    n_pool = 4
+    g = torch.Generator(device=dev).manual_seed(1237 + rank)
+    pool = [0.1 * torch.randn(B, C, L, device=dev, generator=g) for _ in range(n_pool)]
+    first = [shard.clip_checksums(ext(p)) for p in pool]            # also the warm-up (>= 3 calls)
+    last = [None] * n_pool
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.mark()
+    l0 = _abi.lib().seld_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        nb = min(B, n_local - i * B)
+        y = ext(pool[i % n_pool][:nb])
+        if i >= steps - n_pool and nb == B:
+            last[i % n_pool] = y
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = _abi.lib().seld_launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    ok = all(torch.equal(shard.clip_checksums(v), first[j]) for j, v in enumerate(last) if v is not None)
+    okt = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        table = shard.gather_clip_checksums(last[(steps - 2) % n_pool] if steps > 1 else y, B * world)   # cross-rank check: NCCL all_gather
+        finite = bool(torch.isfinite(table).all())
+    else:
+        finite = bool(torch.isfinite(first[0]).all())
+    if rank == 0:
+        sec = float(t[0]) * 1e-3
+        peak, peak_src = measured_peaks()
+        algo = n_chunks * ALGO_BYTES_PER_CLIP
+        emit_json(({
+            'metric': 'audio-seconds/sec (cfg5 epoch sweep)', 'value': n_chunks * CLIP_S / sec, 'unit': UNIT, 'n_gpus': world,
+            'steps': steps, 'warmup': n_pool, 'ms_per_step': sec * 1e3 / steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'cfg5: epoch sweep, 402000 ten-second 4-ch chunks @ 24 kHz (4.02 M audio-s) sharded by chunk, '
+                                   'batches of %d from a resident pool of %d batches per rank (984 MB > L2)' % (B, n_pool)},
+            'epoch_seconds': sec,
+            'roofline': {'bound': 'hbm', 'achieved': algo / sec / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
+                         'frac': algo / sec / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
+                         'algorithmic_bytes_total': algo, 'note': 'per-GPU rate'},
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'pool_results_reproduced_bitwise': bool(okt[0]), 'checksums_finite': finite}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_epilogue(args):
     """SURVEY 8f-1 (extra measurement, 1 GPU): the backbone-input stage on the cfg2 feature map
     (64, 7, 1001, 64) -> (64, 7, 256, 256): fused scalar + fold, the in-place scalar alone, and the
@@ -575,7 +653,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='clips per GPU per step (cfg2: 64)')
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'wav2img', 'augment'],
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg5', 'wav2img', 'augment'],
                     help='cfg2 = BASELINE metric (default); cfg3 = MIC log-mel+GCC B=64; cfg4 = L3DAS22 dual-FOA '
                          '8 ch 32 kHz, global batch 128 sharded by clip (extra measurements, not the headline)')
     ap.add_argument('--cpu-seconds', type=float, default=10.0, help='bound on the cpu_baseline sample')
@@ -583,6 +661,8 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'cfg5':
+        run_epoch(args)
     elif args.workload == 'wav2img':
         run_epilogue(args)
     elif args.workload == 'augment':

@@ -6,7 +6,7 @@ tail -8 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
-for w in cfg3 cfg4 wav2img augment; do
+for w in cfg3 cfg4 cfg5 wav2img augment; do
   timeout 300 python bench.py --workload $w --steps 200 --warmup 20 > gpurun_out/bench_$w.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_$w.json
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --cpu-seconds 0 > gpurun_out/ncu_launch.log 2>&1
