@@ -175,6 +175,24 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps * sample_b * CLIP_S / dt
     sample = '%d of 64 clips per step (10 s, 4 ch, 24 kHz), torch CPU fp32' % sample_b
+    # the same on ONE host thread, one clip (B = 1), median of 5 after 2 warm-ups; and the host CPU
+    torch.set_num_threads(1)
+    x1 = x[:1]
+    t1 = []
+    for i in range(7):
+        t0 = time.perf_counter()
+        torch_port.logmel_iv(x1, win, fb, NFFT, HOP)
+        if i >= 2:
+            t1.append(time.perf_counter() - t0)
+    torch.set_num_threads(threads)
+    cpu_model = None
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                cpu_model = line.split(':', 1)[1].strip()
+                break
+    except OSError:
+        pass
     emit_json(({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
@@ -184,6 +202,9 @@ def run_reference(args):
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'cfg1_one_thread': {'value': CLIP_S / statistics.median(t1), 'unit': UNIT, 'ms_per_clip': 1e3 * statistics.median(t1),
+                            'cores': 1, 'sample': 'one 10-s clip (B = 1), median of 5'},
+        'host_cpu': cpu_model,
     }))
 
 
