@@ -350,6 +350,21 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                     if (vk[f & 3]) ob[ck[f & 3] * ch_stride + (int64_t)tk[f & 3] * M + m] = v;
                 }
             };
+            // Channels 0/1 and 2/3 share a packed transform; a digitally silent one comes out of the untangle step as
+            // its partner's rounding noise (<= -130 dB relative) instead of exact zeros.  For log-mel that hides under
+            // the amin clamp unless the partner is loud, but the normalised intensity vector turns a noise-only I_j
+            // into +-1 when nothing else is there to normalise against (W-only input, or a silent W).  The reference
+            // gives exact zeros in those cases; so a band whose mel power is more than 120 dB under its partner's --
+            // below what the packed fp32 transform resolves -- is set to zero, with the IV rows that depend on it.
+            auto silence_unresolved = [](float (&v)[NR]) {
+                if constexpr (NR == 7) {
+                    constexpr float kRel = 1e-12f;
+                    const bool d0 = v[0] < kRel * v[1], d1 = v[1] < kRel * v[0];
+                    const bool d2 = v[2] < kRel * v[3], d3 = v[3] < kRel * v[2];
+                    v[0] = d0 ? 0.0f : v[0]; v[1] = d1 ? 0.0f : v[1]; v[2] = d2 ? 0.0f : v[2]; v[3] = d3 ? 0.0f : v[3];
+                    v[4] = (d0 || d1) ? 0.0f : v[4]; v[5] = (d0 || d2) ? 0.0f : v[5]; v[6] = (d0 || d3) ? 0.0f : v[6];
+                }
+            };
             if (M <= 64) {
                 // fixed slots: <= 4 runs per segment, run numbers held packed in registers (absent -> the zero run);
                 // all loads are issued up front (a data-dependent slot count was measured 2.4 % slower)
@@ -375,6 +390,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                                     v[f] = ((v0 + v1) + v2) + ((u0 + u1) + u2);
                                 }
                             }
+                            if constexpr (kIV) silence_unresolved(v);
 #pragma unroll
                             for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
                         }
@@ -396,6 +412,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 #pragma unroll
                         for (int f = 0; f < NR; ++f) v[f] += P[f * (kRowWords / 2) + g].x;
                     }
+                    if constexpr (kIV) silence_unresolved(v);
 #pragma unroll
                     for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
                 }

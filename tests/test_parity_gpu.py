@@ -305,3 +305,26 @@ def test_fuzz_shapes_against_oracle():
             ref = (so.logmel_iv if kind == 'logmelIV' else so.logmel)(x, w, fb, 1024, hop, np.float64)
             assert y.shape == ref.shape == (B, C + (3 if kind == 'logmelIV' else 0), 1 + L // hop, 64)
             assert_blocks_close(y, ref, C, what='%s B=%d L=%d hop=%d C=%d' % (kind, B, L, hop, C))
+
+
+@pytest.mark.parametrize('dead', [(1, 2, 3), (0,), (1,), (2,), (3,), (0, 1), (2, 3), (1, 3)])
+def test_digitally_silent_channels(dead):
+    """Exactly-zero channels next to loud ones (W-only / mono-in-FOA input, a dead W, single dead channels).
+    Channels 0/1 and 2/3 share a packed transform, so a silent one is only known down to its partner's rounding
+    noise; the reference gives exact zeros there (log-mel -100 dB, IV 0 where the cross-spectrum vanishes) and so
+    must the kernel -- in particular the normalised IV must not blow that noise up to +-1."""
+    from oracle import seld_oracle as so, synth
+    ext = _ext('logmelIV', 24000, 240, 'hann')
+    x = synth.uniform(300 + sum(dead), (2, 4, 7200)).astype(np.float32)          # loud: full scale +-1
+    x[1] = synth.white(310, 1, 4, 7200)[0]                                        # and an ordinary 0.1-rms clip
+    for c in dead:
+        x[:, c] = 0.0
+    y = _run(ext, x)
+    ref = so.logmel_iv(x, ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy(), 1024, 240, np.float64)
+    assert_blocks_close(y, ref, 4, what='dead channels %s' % (dead,))
+    for c in dead:
+        assert np.abs(y[:, c] + 100.0).max() < 1e-4, 'log-mel of a silent channel is the amin clamp'
+        if c >= 1:
+            assert np.abs(y[:, 3 + c]).max() < 1e-6, 'IV against a silent channel vanishes'
+    if 0 in dead:
+        assert np.abs(y[:, 4:]).max() < 1e-6, 'no W, no intensity'
