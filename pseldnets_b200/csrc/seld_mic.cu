@@ -243,12 +243,14 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             __syncwarp();
             // band per lane; run numbers of segment m (V) and m+1 (U) in fixed slots (absent -> the zero run), all
             // loads issued up front (n_mels == 64 on this path: bands lane and lane + 32)
+            uint32_t quiet = 15u;                                           // bit c: mic c looks silent in both of this lane's bands
             auto combine = [&](auto four_c) {
                 constexpr bool kFour = decltype(four_c)::value;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int m = lane + 32 * r;
                     const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
+                    float v[4];
 #pragma unroll
                     for (int f = 0; f < 4; ++f) {
                         const float* rowp = R + f * kRowWords;
@@ -256,14 +258,21 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                         const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
                         const float u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
                         const float u2 = rowp[2 * ((pu >> 16) & 0xff)];
-                        float v;
                         if constexpr (kFour) {
                             const float v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
-                            v = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
+                            v[f] = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
                         } else {
-                            v = ((v0 + v1) + v2) + ((u0 + u1) + u2);
+                            v[f] = ((v0 + v1) + v2) + ((u0 + u1) + u2);
                         }
-                        const float db = 3.01029995663981195f * __log2f(fmaxf(v, amin));
+                    }
+                    // silent-microphone screen (see below): band power more than 120 dB under the transform partner's
+                    constexpr float kRel = 1e-12f;
+                    const bool d0 = v[0] < kRel * v[1], d1 = v[1] < kRel * v[0], d2 = v[2] < kRel * v[3], d3 = v[3] < kRel * v[2];
+                    quiet &= (d0 ? 1u : 0u) | (d1 ? 2u : 0u) | (d2 ? 4u : 0u) | (d3 ? 8u : 0u);
+                    v[0] = d0 ? 0.0f : v[0]; v[1] = d1 ? 0.0f : v[1]; v[2] = d2 ? 0.0f : v[2]; v[3] = d3 ? 0.0f : v[3];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const float db = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
                         rmax[f] = fmaxf(rmax[f], db);
                         ob[f * ch_stride + m] = db;
                     }
@@ -271,6 +280,19 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             };
             if (four) combine(std::true_type{}); else combine(std::false_type{});
             __syncwarp();                                                   // rows become the exchange buffer again
+            // A microphone whose frame is digitally silent must have an exactly zero spectrum (its cross-spectra then
+            // have angle(0) = 0, phasor 1), but it shares a packed transform with another one (0 with 1, 2 with 3) and
+            // came out of the untangle step as that one's rounding noise, <= -130 dB relative, which PHAT would turn
+            // into random phases.  A microphone more than 120 dB under its partner in every mel band -- below what the
+            // packed fp32 transform resolves -- is taken to be silent: its phasors are cleared (rare path).
+            const uint32_t dead = __reduce_and_sync(0xffffffffu, quiet);
+            if (dead != 0) {
+                for (int c = 0; c < 4; ++c)
+                    if (dead >> c & 1)
+                        for (int k = lane; k <= 512; k += 32) spec[c * kSpecStride + k] = make_float2(0.f, 0.f);
+                min_n = 0.0f;
+                __syncwarp();
+            }
         }
 
         // ---------------- GCC-PHAT.  Two real correlations per complex inverse transform (Z = ph_a + i ph_b):
