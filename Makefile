@@ -15,5 +15,7 @@ bench:            ## one JSON line: audio-s/s, roofline, e2e, CPU baseline
 
 golden:           ## regenerate tests/golden/*.npz from the unmodified reference (build container only)
 	$(PY) tests/golden/make_golden.py
+	$(PY) tests/golden/make_golden_epilogue.py
+	$(PY) tests/golden/make_golden_augment.py
 
 .PHONY: build test-cpu test-gpu bench golden
