@@ -129,6 +129,24 @@ def bind_to_gpu_numa_node(local_rank):
         return False
 
 
+def library_ops_same_gpu(x, window, fb):
+    """The reference's op sequence on whatever device x lives on -- feature.py:46-56 + 101-115 as the library calls
+    they resolve to (torch.stft with reflect centre padding, |X|^2, (T,F)@(F,M), 10*log10(clamp), three real cross
+    terms / norm, three more matmuls, cat).  Used for the same-GPU library baseline only."""
+    import torch
+    B, Cn, Ln = x.shape
+    X = torch.stft(x.reshape(-1, Ln), n_fft=NFFT, hop_length=HOP, win_length=NFFT, window=window, center=True,
+                   pad_mode='reflect', normalized=False, onesided=True, return_complex=True)
+    X = X.reshape(B, Cn, X.shape[-2], X.shape[-1])                              # (B, C, F, T)
+    mel = torch.matmul((torch.abs(X) ** 2).transpose(-1, -2), fb)                # (B, C, T, M)
+    logmel = 10.0 * torch.log10(torch.clamp(mel, min=1e-10))
+    re, im = X.real.transpose(-1, -2), X.imag.transpose(-1, -2)
+    cross = [re[:, 0] * re[:, j] + im[:, 0] * im[:, j] for j in (1, 2, 3)]
+    norm = torch.sqrt(cross[0] ** 2 + cross[1] ** 2 + cross[2] ** 2) + torch.finfo(torch.float32).eps
+    iv = torch.stack([torch.matmul(c / norm, fb) for c in cross], dim=1)
+    return torch.cat((logmel, iv), dim=1)
+
+
 def cpu_port_throughput(batch, min_seconds, max_calls, threads):
     """The reference's CPU path (oracle/torch_port.py: same torch.stft / matmul calls as the
     reference makes through torchaudio) on the host cores.  Returns (audio-s/s, calls, seconds)."""
@@ -602,15 +620,16 @@ def run_ours(args):
         if world == 1 and args.cpu_seconds > 0:
             # the reference's op sequence (torch.stft -> |X|^2 -> matmul -> log10, IV arithmetic: cuFFT, cuBLAS
             # and ~45 ATen launches) on the SAME GPU and batch -- the library baseline the fused kernel replaces
-            from oracle import torch_port
             win_d, fb_d = ext.stft_extractor.window, ext.mel_scale.fb
-            for _ in range(2):
-                y_lib = torch_port.logmel_iv(x, win_d, fb_d, NFFT, HOP)
+            with torch.no_grad():
+                for _ in range(2):
+                    y_lib = library_ops_same_gpu(x, win_d, fb_d)
             torch.cuda.synchronize()
             l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0.record()
-            for _ in range(5):
-                y_lib = torch_port.logmel_iv(x, win_d, fb_d, NFFT, HOP)
+            with torch.no_grad():
+                for _ in range(5):
+                    y_lib = library_ops_same_gpu(x, win_d, fb_d)
             l1.record()
             torch.cuda.synchronize()
             lib_ms = l0.elapsed_time(l1) / 5
