@@ -227,3 +227,22 @@ def test_augment_abi_argument_checks_without_gpu():
     assert l.seld_wavmix_f32(None, 2, 4, 100, 400, 100, None, 1, None) == _abi.SELD_EINVAL
     assert l.seld_wavmix_order(None, None, None, 0, 4, None) == _abi.SELD_OK
     assert l.seld_wavmix_order(None, None, None, 1, 4, None) == _abi.SELD_EINVAL
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """The driver contract: `bench.py --impl reference` prints exactly ONE JSON line on stdout with the agreed keys
+    (everything else a library may print goes to stderr)."""
+    import json
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['unit'] == 'audio-s/s' and d['higher_is_better'] is True
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['value'] > 0
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and 'workload' in d['config']
