@@ -328,3 +328,30 @@ def test_digitally_silent_channels(dead):
             assert np.abs(y[:, 3 + c]).max() < 1e-6, 'IV against a silent channel vanishes'
     if 0 in dead:
         assert np.abs(y[:, 4:]).max() < 1e-6, 'no W, no intensity'
+
+
+def test_bench_prints_one_json_line_with_the_contract_keys():
+    """bench.py on one GPU, short run: exactly ONE JSON line on stdout carrying the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '20', '--warmup', '5', '--cpu-seconds', '1'],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout[:2000]
+    d = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'cpu_baseline', 'e2e', 'gpu_launches', 'clocks'):
+        assert key in d, key
+    assert d['n_gpus'] == 1 and d['steps'] == 20 and d['warmup'] >= 3 and d['dtype'] == 'f32' and d['vs_baseline'] is None
+    r = d['roofline']
+    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] > 0
+    e = d['e2e']
+    assert e['h2d_bytes_per_step'] == 64 * 4 * 240000 * 4 and e['d2h_bytes_per_step'] == 64 * 7 * 1001 * 64 * 4
+    assert 0 < e['value'] < d['value'] and e['matches_resident_path'] is True
+    assert d['gpu_launches'] == 20 and 'workload' in d['config'] and d['outputs_finite'] is True
+    assert d['clocks']['sm_mhz'] and d['clocks']['samples'] >= 1
