@@ -33,9 +33,13 @@ __device__ unsigned long long g_phase_cycles[16];
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
-constexpr int kRowWords = 528;            // 33 chunks of 16 bins (bin 512 opens chunk 32)
+// Rows are kept in PAIRS, interleaved as float2 per bin, the way the untangle step produces them:
+//   pair 0 = (P0, P2), pair 1 = (P1, P3), pair 2 = (n1, n3), pair 3 = (n2, -)       (log-mel only: pairs 0 and 1)
+// so the mel walk and the combine step handle two rows per packed instruction.
+constexpr int kPairWords = 1056;          // 33 chunks of 16 bins x float2 (bin 512 opens chunk 32)
+constexpr int kPairs = 4;
 constexpr int kRows = 7;                  // P0 P1 P2 P3 n1 n2 n3 (log-mel only: the first 4)
-constexpr int kRegion = kRows * kRowWords;   // floats per warp; the 32x33 float2 exchange buffer (2112) aliases it
+constexpr int kRegion = kPairs * kPairWords; // floats per warp; the 32x34 float2 exchange buffer (2176) aliases it
 constexpr int kZeroRun = 127;             // float2 slot of every row kept at (0, 0) during the combine step
 constexpr int kTwStride = 68;             // 32 float2 + pad
 constexpr int kWinStride = 36;            // 32 floats + pad
@@ -79,14 +83,14 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     const int g0 = pd.g0[lane];
     const int hop = pd.hop, M = pd.n_mels;
     const float eps = pd.eps, amin = pd.amin, in_scale = a.in_scale;
-    // writer: bin k = lane + 32*kb lands at word 32*kb + wofs[kb & 3] of its row
+    // A pair-row is cut in chunks of 16 bins = 128 bytes; the 16-byte sub-chunk s (two bins) of chunk c is stored at
+    // position s ^ (c & 7), which makes both sides conflict-free:
+    // writer: bin k = lane + 32*kb (chunk 2*kb + lane/16) lands at word 64*kb + wofs[kb & 3] of its pair-row
     int wofs[4];
 #pragma unroll
-    for (int x = 0; x < 4; ++x) wofs[x] = 16 * (lane >> 4) + 4 * (((lane >> 2) & 3) ^ x) + (lane & 3);
-    // reader: lane owns chunk c = lane; logical quad i sits at word 16c + 4*(i ^ ((c >> 1) & 3))
-    int rofs[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) rofs[i] = 16 * lane + 4 * (i ^ ((lane >> 1) & 3));
+    for (int x = 0; x < 4; ++x)
+        wofs[x] = 32 * (lane >> 4) + 4 * ((((lane & 15) >> 1) ^ ((2 * x + (lane >> 4)) & 7))) + 2 * (lane & 1);
+    // reader: lane owns chunk c = lane; its logical sub-chunk i sits at word 32c + 4*(i ^ (c & 7)) (computed per frame)
 
     const int64_t ch_stride = (int64_t)a.T * M;
     // combine step, bands lane and lane+32: run numbers of segment m (V) and m+1 (U), four slots each
@@ -266,22 +270,17 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                     const float nrm = (s > 1e-37f ? s * rsqrt_ftz(s) : 0.0f) + eps;
                     const float inv = rcp_ftz(nrm);
                     if (kb < 16 || lane == 0) {
-                        float* q = R + 32 * kb + wofs[kb & 3];
-                        q[0 * kRowWords] = p02.x;
-                        q[1 * kRowWords] = p13.x;
-                        q[2 * kRowWords] = p02.y;
-                        q[3 * kRowWords] = p13.y;
-                        q[4 * kRowWords] = i13.x * inv;
-                        q[5 * kRowWords] = i2 * inv;
-                        q[6 * kRowWords] = i13.y * inv;
+                        float2* q = reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
+                        q[0 * (kPairWords / 2)] = p02;
+                        q[1 * (kPairWords / 2)] = p13;
+                        q[2 * (kPairWords / 2)] = vmuls(i13, inv);
+                        q[3 * (kPairWords / 2)] = make_float2(i2 * inv, 0.0f);
                     }
                 } else {
                     if (kb < 16 || lane == 0) {
-                        float* q = R + 32 * kb + wofs[kb & 3];
-                        q[0 * kRowWords] = p02.x;
-                        q[1 * kRowWords] = p13.x;
-                        q[2 * kRowWords] = p02.y;
-                        q[3 * kRowWords] = p13.y;
+                        float2* q = reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
+                        q[0 * (kPairWords / 2)] = p02;
+                        q[1 * (kPairWords / 2)] = p13;
                     }
                 }
             });
@@ -291,6 +290,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         PHASE_MARK(6);   // pointwise
         // ---------------- mel step 1: chunk walk of all rows, per-run partial sums (U, V) left in the rows
         constexpr int NR = kIV ? kRows : 4;
+        constexpr int NP = kIV ? kPairs : 2;                                // pair-rows in use
         {
             float2 wv[17];
             const float4* wp = reinterpret_cast<const float4*>(wab_s + lane * kWabStride);
@@ -301,38 +301,45 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 wv[2 * i + 1] = make_float2(v.z, v.w);
             }
             wv[16] = *reinterpret_cast<const float2*>(wab_s + lane * kWabStride + 32);
-            float q[NR][17];
+            float2 q[NP][17];                                               // (row, row') values of the lane's 16 (+1) bins
 #pragma unroll
-            for (int f = 0; f < NR; ++f) {
-                const float* row = R + f * kRowWords;
+            for (int f = 0; f < NP; ++f) {
+                const float* row = R + f * kPairWords;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(row + rofs[i]);
-                    q[f][4 * i] = v.x; q[f][4 * i + 1] = v.y; q[f][4 * i + 2] = v.z; q[f][4 * i + 3] = v.w;
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + 32 * lane + 4 * (i ^ (lane & 7)));
+                    q[f][2 * i] = make_float2(v.x, v.y); q[f][2 * i + 1] = make_float2(v.z, v.w);
                 }
-                q[f][16] = lane == 31 ? row[512] : 0.0f;
+                q[f][16] = lane == 31 ? *reinterpret_cast<const float2*>(row + 1024) : make_float2(0.0f, 0.0f);
             }
             __syncwarp();                                                   // everyone holds its bins: rows may be overwritten
-            if (lane < NR) reinterpret_cast<float2*>(R + lane * kRowWords)[kZeroRun] = make_float2(0.f, 0.f);
-            float2 acc[NR];
-            float2* po = reinterpret_cast<float2*>(R) + g0;
+            if (lane < NP) reinterpret_cast<float4*>(R + lane * kPairWords)[kZeroRun] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // per pair-row: U = sum a_k q_k and V = sum b_k q_k of the current run, each for both rows of the pair
+            float2 U[NP], V[NP];
+            float4* po = reinterpret_cast<float4*>(R) + g0;                 // slot of run r: words 4r..4r+3 = (U, U', V, V')
+            {
+                const float2 aa = make_float2(wv[0].x, wv[0].x), bb = make_float2(wv[0].y, wv[0].y);
 #pragma unroll
-            for (int f = 0; f < NR; ++f) acc[f] = vmuls(wv[0], q[f][0]);
-            // branch-free: where a new run starts the finished pair is stored and the accumulator restarts
-            // (acc * keep with keep = 0); one FMUL2 + one FFMA2 + one predicated store per bin and row
+                for (int f = 0; f < NP; ++f) { U[f] = __fmul2_rn(aa, q[f][0]); V[f] = __fmul2_rn(bb, q[f][0]); }
+            }
+            // branch-free: where a new run starts the finished sums are stored and the accumulators restart
+            // (acc * keep with keep = 0); the weights are broadcast once per bin for all rows
             static_for<1, 17>([&](auto ji) {
                 constexpr int j = decltype(ji)::value;
                 const bool start = (runmask >> j) & 1u;
                 const float keep = start ? 0.0f : 1.0f;
+                const float2 kk = make_float2(keep, keep);
+                const float2 aa = make_float2(wv[j].x, wv[j].x), bb = make_float2(wv[j].y, wv[j].y);
 #pragma unroll
-                for (int f = 0; f < NR; ++f) {
-                    if (start) po[f * (kRowWords / 2)] = acc[f];
-                    acc[f] = __ffma2_rn(wv[j], make_float2(q[f][j], q[f][j]), vmuls(acc[f], keep));
+                for (int f = 0; f < NP; ++f) {
+                    if (start) po[f * (kPairWords / 4)] = make_float4(U[f].x, U[f].y, V[f].x, V[f].y);
+                    U[f] = __ffma2_rn(aa, q[f][j], __fmul2_rn(U[f], kk));
+                    V[f] = __ffma2_rn(bb, q[f][j], __fmul2_rn(V[f], kk));
                 }
                 po += start ? 1 : 0;
             });
 #pragma unroll
-            for (int f = 0; f < NR; ++f) po[f * (kRowWords / 2)] = acc[f];
+            for (int f = 0; f < NP; ++f) po[f * (kPairWords / 4)] = make_float4(U[f].x, U[f].y, V[f].x, V[f].y);
         }
         __syncwarp();
 
@@ -375,21 +382,24 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                         const int m = lane + 32 * r;
                         if (m < M) {
                             const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
-                            float v[NR];
+                            float2 vv[NP];                                  // both rows of a pair per packed add
 #pragma unroll
-                            for (int f = 0; f < NR; ++f) {
-                                const float* rowp = R + f * kRowWords;
-                                const float v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
-                                const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
-                                const float u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
-                                const float u2 = rowp[2 * ((pu >> 16) & 0xff)];
+                            for (int f = 0; f < NP; ++f) {
+                                const float2* rowp = reinterpret_cast<const float2*>(R + f * kPairWords);   // slot r: [2r] = U pair, [2r+1] = V pair
+                                const float2 v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
+                                const float2 v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
+                                const float2 u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
+                                const float2 u2 = rowp[2 * ((pu >> 16) & 0xff)];
                                 if constexpr (kFour) {
-                                    const float v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
-                                    v[f] = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
+                                    const float2 v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
+                                    vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, v3)), vadd(vadd(u0, u1), vadd(u2, u3)));
                                 } else {
-                                    v[f] = ((v0 + v1) + v2) + ((u0 + u1) + u2);
+                                    vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
                                 }
                             }
+                            float v[NR];
+                            v[0] = vv[0].x; v[2] = vv[0].y; v[1] = vv[1].x; v[3] = vv[1].y;
+                            if constexpr (kIV) { v[4] = vv[2].x; v[6] = vv[2].y; v[5] = vv[3].x; }
                             if constexpr (kIV) silence_unresolved(v);
 #pragma unroll
                             for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
@@ -398,20 +408,23 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 };
                 if (four) combine(std::true_type{}); else combine(std::false_type{});
             } else {
-                const float2* P = reinterpret_cast<const float2*>(R);
+                const float4* P = reinterpret_cast<const float4*>(R);        // slot g of pair-row f: (U, U', V, V')
                 for (int m = lane; m < M; m += 32) {
                     const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
-                    float v[NR];
+                    float2 vv[NP];
 #pragma unroll
-                    for (int f = 0; f < NR; ++f) v[f] = 0.0f;
+                    for (int f = 0; f < NP; ++f) vv[f] = make_float2(0.0f, 0.0f);
                     for (int g = ga; g < gb; ++g) {
 #pragma unroll
-                        for (int f = 0; f < NR; ++f) v[f] += P[f * (kRowWords / 2) + g].y;
+                        for (int f = 0; f < NP; ++f) { const float4 t = P[f * (kPairWords / 4) + g]; vv[f] = vadd(vv[f], make_float2(t.z, t.w)); }
                     }
                     for (int g = gb; g < gc; ++g) {
 #pragma unroll
-                        for (int f = 0; f < NR; ++f) v[f] += P[f * (kRowWords / 2) + g].x;
+                        for (int f = 0; f < NP; ++f) { const float4 t = P[f * (kPairWords / 4) + g]; vv[f] = vadd(vv[f], make_float2(t.x, t.y)); }
                     }
+                    float v[NR];
+                    v[0] = vv[0].x; v[2] = vv[0].y; v[1] = vv[1].x; v[3] = vv[1].y;
+                    if constexpr (kIV) { v[4] = vv[2].x; v[6] = vv[2].y; v[5] = vv[3].x; }
                     if constexpr (kIV) silence_unresolved(v);
 #pragma unroll
                     for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
