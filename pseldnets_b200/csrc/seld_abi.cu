@@ -241,7 +241,7 @@ static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C,
     if (!x || !out) return SELD_EINVAL;
     const int64_t T = 1 + L / p->dev.hop;
     if (T > INT32_MAX) return SELD_EUNSUPPORTED;
-    seld::FoaArgs a;
+    seld::FoaArgs a{};
     a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
     a.B = (int)B; a.C = C; a.Cout = C + (iv ? 3 : 0); a.T = (int)T; a.c_lo = 0;
     a.span = 0; a.vec_ok = 0; a.in_i16 = i16 ? 1 : 0; a.in_scale = i16 ? 1.0f / 32768.0f : 1.0f;
@@ -405,7 +405,7 @@ extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B
     const int fpt = seld::mic_frames_per_tile();
     const int64_t tpc = (T + fpt - 1) / fpt;
     if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
-    seld::FoaArgs a;
+    seld::FoaArgs a{};
     a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
     a.B = (int)B; a.C = C; a.Cout = C + C * (C - 1) / 2; a.T = (int)T; a.c_lo = 0;
     a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.span = 0; a.vec_ok = 0; a.in_i16 = 0; a.in_scale = 1.0f;

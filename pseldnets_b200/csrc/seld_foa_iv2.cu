@@ -112,9 +112,16 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     long long phase_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long phase_t0 = clock64();
 #endif
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_clip;
-        const int grp = (tile - b * a.tiles_per_clip) * W + warp;           // kIV: the frame; else: group of 4 jobs
+    // tile = (clip tb, tile tr within the clip), advanced by the grid size without a division per frame (the
+    // division was a 500-cycle dependent chain at the top of every frame)
+    int tb = blockIdx.x / a.tiles_per_clip, tr = blockIdx.x - tb * a.tiles_per_clip;
+    auto next_tile = [&]() {
+        tb += a.step_clip; tr += a.step_tile;
+        if (tr >= a.tiles_per_clip) { tr -= a.tiles_per_clip; ++tb; }
+    };
+    for (; tb < a.B; next_tile()) {
+        const int b = tb;
+        const int grp = tr * W + warp;                                      // kIV: the frame; else: group of 4 jobs
         int tk[4] = {0, 0, 0, 0}, ck[4] = {0, 0, 0, 0};                     // log-mel only: frame / channel of each transform slot
         bool vk[4] = {true, true, true, true};
         if constexpr (kIV) {
@@ -468,7 +475,9 @@ static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_coun
     cudaError_t e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
-    foa_iv2_kernel<W, TIn, kIV><<<gx, W * 32, smem, st>>>(a, pd);
+    FoaArgs aa = a;
+    aa.step_clip = gx / a.tiles_per_clip; aa.step_tile = gx - aa.step_clip * a.tiles_per_clip;
+    foa_iv2_kernel<W, TIn, kIV><<<gx, W * 32, smem, st>>>(aa, pd);
     return cudaGetLastError();
 }
 

@@ -41,6 +41,7 @@ struct FoaArgs {
     int B, C, Cout, T;       // C = channels of x, Cout = channels of out
     int c_lo;                // first input channel this launch covers (log-mel of channels c_lo..C-1)
     int tiles_per_clip, n_tiles;
+    int step_clip, step_tile;  // iv2: grid size split as step_clip * tiles_per_clip + step_tile (set by the launcher)
     int span;                // staged samples per channel per tile (multiple of 4)
     int vec_ok;              // x base/strides allow 16-byte loads
 };
