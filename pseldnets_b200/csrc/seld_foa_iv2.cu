@@ -320,10 +320,12 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 q[f][16] = lane == 31 ? *reinterpret_cast<const float2*>(row + 1024) : make_float2(0.0f, 0.0f);
             }
             __syncwarp();                                                   // everyone holds its bins: rows may be overwritten
+            PHASE_MARK(9);   // walk: weights + rows in registers
             if (lane < NP) reinterpret_cast<float4*>(R + lane * kPairWords)[kZeroRun] = make_float4(0.f, 0.f, 0.f, 0.f);
             // per pair-row: U = sum a_k q_k and V = sum b_k q_k of the current run, each for both rows of the pair
             float2 U[NP], V[NP];
-            float4* po = reinterpret_cast<float4*>(R) + g0;                 // slot of run r: words 4r..4r+3 = (U, U', V, V')
+            float2* po = reinterpret_cast<float2*>(R) + 2 * g0;             // slot of run r: words 4r..4r+3 = (U, U', V, V'), two 64-bit stores
+                                                                            // (one 128-bit store would need the four values moved into an aligned register quad)
             {
                 const float2 aa = make_float2(wv[0].x, wv[0].x), bb = make_float2(wv[0].y, wv[0].y);
 #pragma unroll
@@ -339,14 +341,14 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 const float2 aa = make_float2(wv[j].x, wv[j].x), bb = make_float2(wv[j].y, wv[j].y);
 #pragma unroll
                 for (int f = 0; f < NP; ++f) {
-                    if (start) po[f * (kPairWords / 4)] = make_float4(U[f].x, U[f].y, V[f].x, V[f].y);
+                    if (start) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
                     U[f] = __ffma2_rn(aa, q[f][j], __fmul2_rn(U[f], kk));
                     V[f] = __ffma2_rn(bb, q[f][j], __fmul2_rn(V[f], kk));
                 }
-                po += start ? 1 : 0;
+                po += start ? 2 : 0;
             });
 #pragma unroll
-            for (int f = 0; f < NP; ++f) po[f * (kPairWords / 4)] = make_float4(U[f].x, U[f].y, V[f].x, V[f].y);
+            for (int f = 0; f < NP; ++f) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
         }
         __syncwarp();
 

@@ -32,9 +32,9 @@ torch.cuda.synchronize()
 lib.seld_dev_phase_cycles(buf, 0)
 frames = 64 * 1001 * N
 names = ['loop/index', 'issue loads', 'loads land + window', 'fft32 #1', 'twiddle + exchange', 'fft32 #2', 'pointwise -> rows',
-         'mel walk', 'mel combine + store', '-']
-tot = sum(buf[i] for i in range(9))
+         'mel walk (accumulate)', 'mel combine + store', 'mel walk (load rows)']
+tot = sum(buf[i] for i in range(10))
 print('kernel %.1f us (timing build)' % (1e3 * e0.elapsed_time(e1) / N))
-for i in range(9):
+for i in range(10):
     print('%-22s %8.0f cycles/frame  %5.1f%%' % (names[i], buf[i] / frames, 100.0 * buf[i] / tot))
 print('%-22s %8.0f cycles/frame' % ('total per warp-frame', tot / frames))
