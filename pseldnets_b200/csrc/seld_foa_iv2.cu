@@ -48,6 +48,7 @@ constexpr int kWabStride = 36;            // floats per lane in the (a, b) weigh
 
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // TIn = float (the reference's input) or int16_t (PCM as decoded from wav/flac: soundfile's float32
 // conversion is s / 32768, folded exactly into the window: a.in_scale = 2^-15)
@@ -250,6 +251,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         // ---------------- per-bin quantities -> 7 rows
         {
             const int src = (32 - lane) & 31;
+            const bool lane0 = lane == 0;
             static_for<0, 17>([&](auto kbi) {
                 constexpr int kb = decltype(kbi)::value;
                 constexpr int p = brev5(kb & 31);
@@ -259,11 +261,11 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                     pr = zr; pi = zi;
                 } else {
                     constexpr int pp = brev5(31 - kb), p0 = brev5((32 - kb) & 31);
-                    pr.x = __shfl_sync(0xffffffffu, re[pp].x, src);
-                    pr.y = __shfl_sync(0xffffffffu, re[pp].y, src);
-                    pi.x = __shfl_sync(0xffffffffu, im[pp].x, src);
-                    pi.y = __shfl_sync(0xffffffffu, im[pp].y, src);
-                    if (lane == 0) { pr = re[p0]; pi = im[p0]; }
+                    // lane 0 holds its own partners (bins 32*kb <-> 32*(32-kb)); written as selects so that each costs one FSEL
+                    const float sx = __shfl_sync(0xffffffffu, re[pp].x, src), sy = __shfl_sync(0xffffffffu, re[pp].y, src);
+                    const float tx = __shfl_sync(0xffffffffu, im[pp].x, src), ty = __shfl_sync(0xffffffffu, im[pp].y, src);
+                    pr = make_float2(lane0 ? re[p0].x : sx, lane0 ? re[p0].y : sy);
+                    pi = make_float2(lane0 ? im[p0].x : tx, lane0 ? im[p0].y : ty);
                 }
                 // window was pre-scaled by 0.5: A = Z[k] + conj(Z[N-k]), B = (Z[k] - conj(Z[N-k])) / i
                 const float2 ar = vadd(zr, pr), ai = vsub(zi, pi);          // (X0, X2)
@@ -274,7 +276,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                     const float2 i13 = vfmas(bi, ai.x, vmuls(br, ar.x));    // Re(conj(X0) X1), Re(conj(X0) X3)
                     const float i2 = fmaf(ai.x, ai.y, ar.x * ar.y);         // Re(conj(X0) X2)
                     const float s = fmaf(i13.y, i13.y, fmaf(i2, i2, i13.x * i13.x));
-                    const float nrm = (s > 1e-37f ? s * rsqrt_ftz(s) : 0.0f) + eps;
+                    const float nrm = sqrt_ftz(s) + eps;                     // one MUFU; sqrt(0) = 0, subnormal sums flush to 0 (far below eps)
                     const float inv = rcp_ftz(nrm);
                     if (kb < 16 || lane == 0) {
                         float2* q = reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
