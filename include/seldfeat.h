@@ -33,7 +33,7 @@ typedef struct seld_plan seld_plan;
  * Stands in for LogmelIV_Extractor.__init__ / Logmel_Extractor.__init__ (feature.py:21-37,
  * 60-75): `window_host` is the (n_fft,) analysis window the reference keeps as
  * `stft_extractor.window`, `fb_host` the (n_fft/2+1, n_mels) row-major mel bank it keeps as
- * `mel_scale.fb`; amin is AmplitudeToDB's clamp (1e-10), eps the intensity-vector epsilon
+ * `mel_scale.fb`; amin is AmplitudeToDB's clamp (1e-10; values below FLT_MIN are raised to it), eps the intensity-vector epsilon
  * (feature.py:8).  Allocates device memory; not on the per-step path. */
 int seld_plan_create(seld_plan** plan, int device, const float* window_host, const float* fb_host,
                      int n_fft, int hop, int n_mels, float amin, float eps);

@@ -26,6 +26,12 @@ inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x,
 
 namespace seld {
 
+#ifdef __CUDACC__
+// log2 of a normal positive number in one MUFU (__log2f adds a compare, a scale and a correction for subnormal
+// arguments; the kernels only take it of max(v, amin) with amin >= FLT_MIN)
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
     if constexpr (I < N) {

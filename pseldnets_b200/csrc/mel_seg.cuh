@@ -105,7 +105,7 @@ __device__ __forceinline__ void mel_combine(const float* R, const int* gseg_s, i
         }
 #pragma unroll
         for (int f = 0; f < NF; ++f)
-            o[f][m] = kDb ? 3.01029995663981195f * __log2f(fmaxf(v[f], amin)) : v[f];   // 10*log10(max(v, amin))
+            o[f][m] = kDb ? 3.01029995663981195f * lg2_ftz(fmaxf(v[f], amin)) : v[f];   // 10*log10(max(v, amin))
     }
 }
 

@@ -187,7 +187,7 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     p->dev.fast_ok = fast_ok;
     p->dev.nnz_pad = (int)wt.size();
     p->dev.n_mels = n_mels; p->dev.n_mels_pad = n_mels_pad;
-    p->dev.hop = hop; p->dev.amin = amin; p->dev.eps = eps;
+    p->dev.hop = hop; p->dev.amin = amin < 1.17549435e-38f ? 1.17549435e-38f : amin; p->dev.eps = eps;   // the kernels take log2 of max(v, amin) with a flush-to-zero MUFU: amin below FLT_MIN is raised to it
 
     // the tile (frames_per_tile-1)*hop + n_fft samples x 4 channels must fit next to the tables
     const int span = (((seld::foa_frames_per_tile() - 1) * hop + n_fft) + 3) & ~3;

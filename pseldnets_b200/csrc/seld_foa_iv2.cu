@@ -68,11 +68,12 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float in_scale = a.in_scale;
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
         const float2 w = pd.tw[brev5(r) * 32 + l];
         tw_s[l * kTwStride + 2 * r] = w.x; tw_s[l * kTwStride + 2 * r + 1] = w.y;
-        win_s[l * kWinStride + r] = pd.win[i];
+        win_s[l * kWinStride + r] = pd.win[i] * in_scale;                   // int16 PCM: the 2^-15 of soundfile's conversion, exact
     }
     for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
     for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
@@ -83,7 +84,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     const uint32_t runmask = pd.runmask[lane];
     const int g0 = pd.g0[lane];
     const int hop = pd.hop, M = pd.n_mels;
-    const float eps = pd.eps, amin = pd.amin, in_scale = a.in_scale;
+    const float eps = pd.eps, amin = pd.amin;
     // A pair-row is cut in chunks of 16 bins = 128 bytes; the 16-byte sub-chunk s (two bins) of chunk c is stored at
     // position s ^ (c & 7), which makes both sides conflict-free:
     // writer: bin k = lane + 32*kb (chunk 2*kb + lane/16) lands at word 64*kb + wofs[kb & 3] of its pair-row
@@ -204,7 +205,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         static_for<0, 8>([&](auto mi) {
             constexpr int m4 = decltype(mi)::value;
             const float4 w4 = *reinterpret_cast<const float4*>(win_s + lane * kWinStride + 4 * m4);
-            const float w[4] = {w4.x * in_scale, w4.y * in_scale, w4.z * in_scale, w4.w * in_scale};
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 re[4 * m4 + e] = vmuls(re[4 * m4 + e], w[e]);
@@ -361,7 +362,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             // IV channels of frame t; log-mel only: (channel, frame) of slot f, if that slot holds a job
             float* const ob = a.out + ((int64_t)b * a.Cout) * ch_stride + (kIV ? (int64_t)t * M : 0);
             auto emit = [&](int f, int m, float v) {
-                if (f < 4) v = 3.01029995663981195f * __log2f(fmaxf(v, amin));   // 10*log10(max(v, amin))
+                if (f < 4) v = 3.01029995663981195f * lg2_ftz(fmaxf(v, amin));   // 10*log10(max(v, amin))
                 if constexpr (kIV) {
                     ob[(f < 4 ? f : a.C + f - 4) * ch_stride + m] = v;
                 } else {

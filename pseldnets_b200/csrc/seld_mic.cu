@@ -272,7 +272,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     v[0] = d0 ? 0.0f : v[0]; v[1] = d1 ? 0.0f : v[1]; v[2] = d2 ? 0.0f : v[2]; v[3] = d3 ? 0.0f : v[3];
 #pragma unroll
                     for (int f = 0; f < 4; ++f) {
-                        const float db = 3.01029995663981195f * __log2f(fmaxf(v[f], amin));
+                        const float db = 3.01029995663981195f * lg2_ftz(fmaxf(v[f], amin));
                         rmax[f] = fmaxf(rmax[f], db);
                         ob[f * ch_stride + m] = db;
                     }
