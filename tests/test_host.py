@@ -246,3 +246,43 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d['impl'] == 'reference' and d['unit'] == 'audio-s/s' and d['higher_is_better'] is True
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['value'] > 0
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and 'workload' in d['config']
+
+
+def test_paired_row_layout_of_the_iv2_kernel():
+    """Index algebra of the pair-rows in csrc/seld_foa_iv2.cu (restated here): the untangle step, which holds bin
+    lane + 32*kb, and the mel walk, which wants bins 16*lane .. 16*lane + 15, must address the same float2 for the
+    same bin, injectively, and both access patterns must be free of shared-memory bank conflicts."""
+    K_PAIR_WORDS = 1056
+
+    def writer_word(lane, kb):                      # float2 of bin lane + 32*kb: word 64*kb + wofs[kb & 3]
+        x = kb & 3
+        wofs = 32 * (lane >> 4) + 4 * ((((lane & 15) >> 1) ^ ((2 * x + (lane >> 4)) & 7))) + 2 * (lane & 1)
+        return 64 * kb + wofs
+
+    def reader_word(lane, j):                       # bin 16*lane + j: sub-chunk i = j >> 1 at 32*lane + 4*(i ^ (lane & 7))
+        return 32 * lane + 4 * ((j >> 1) ^ (lane & 7)) + 2 * (j & 1)
+
+    where = {}
+    for kb in range(17):
+        for lane in range(32 if kb < 16 else 1):
+            k = lane + 32 * kb
+            w = writer_word(lane, kb)
+            assert 0 <= w and w + 1 < K_PAIR_WORDS
+            where[k] = w
+    assert len(set(where.values())) == 513                                     # injective
+    for k in range(512):
+        assert where[k] == reader_word(k >> 4, k & 15), k
+    assert where[512] == 1024                                                   # lane 31 reads it at row + 1024
+    # STS.64 of the untangle step: each half-warp's 16 stores cover 32 distinct banks (2 wavefronts per store)
+    for kb in range(16):
+        for half in range(2):
+            banks = set()
+            for lane in range(16 * half, 16 * half + 16):
+                w = writer_word(lane, kb)
+                banks.update({w % 32, (w + 1) % 32})
+            assert len(banks) == 32
+    # LDS.128 of the walk: the 8 lanes of a phase hit 8 different 16-byte bank groups
+    for i in range(8):
+        for phase in range(4):
+            groups = {((32 * lane + 4 * (i ^ (lane & 7))) % 32) // 4 for lane in range(8 * phase, 8 * phase + 8)}
+            assert len(groups) == 8
