@@ -11,7 +11,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libseldfeat.so')
-SOURCES = ['seld_foa.cu', 'seld_foa_iv2.cu', 'seld_foa_iv3.cu', 'seld_mic.cu', 'seld_epilogue.cu', 'seld_augment.cu', 'seld_abi.cu']
+SOURCES = ['seld_foa.cu', 'seld_foa_iv2.cu', 'seld_mic.cu', 'seld_epilogue.cu', 'seld_augment.cu', 'seld_abi.cu']
+# SELD_EXPERIMENTS=1 python -m pseldnets_b200.build  adds the kernels that lost their A/B runs (tensor-core mel
+# projection iv5, two-warps-per-frame iv3, 12-warp iv2), selectable with SELD_IV_KERNEL=5 / 3 / SELD_IV2_WARPS=12;
+# the product library ships without them.
+EXPERIMENT_SOURCES = ['seld_foa_iv5.cu', 'seld_foa_iv3.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -29,8 +33,10 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    experiments = os.environ.get('SELD_EXPERIMENTS', '') not in ('', '0')
+    sources = SOURCES + (EXPERIMENT_SOURCES if experiments else [])
+    cmd = [nvcc] + NVCC_FLAGS + (['-DSELD_EXPERIMENTS'] if experiments else []) + (['-Xptxas', '-v'] if verbose else []) + \
+          ['-o', LIB] + [os.path.join(CSRC, s) for s in sources]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)

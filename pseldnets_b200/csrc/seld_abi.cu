@@ -29,8 +29,11 @@ struct seld_plan {
     int sm_count;
     int n_fft;
     size_t smem_optin;
-    int iv_kernel;         // 3 / 2: generation of the 4-channel IV kernel in use; 0: general kernel only
-    bool use_iv2;          // segment-form bank + shared memory fit: 4-channel IV goes to the iv2 kernel
+    seld::MelTiles mt;     // mel bank as tensor-core operand (iv5)
+    int iv_kernel;         // 5 / 3 / 2: generation of the 4-channel IV kernel in use; 0: general kernel only
+    bool use_iv2;          // a fused 4-channel IV kernel (iv2 / iv3 / iv5) is in use
+    bool iv2_ok;           // the fp32 mel-walk kernel can take this bank (fallback of iv5 for unaligned outputs)
+    bool lm4_ok;           // log-mel-only mode of the iv2 kernel available (channels beyond the first four, Logmel_Extractor)
     void* blob;            // one device allocation holding every table
 };
 
@@ -132,6 +135,45 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
             win2[(q * 32 + l) * 2 + 1] = win[32 * (2 * q + 1) + l];
         }
 
+    // ---- the bank as tensor-core B operand (iv5): 33 chunks of 16 bins, K-major unswizzled bf16 tiles holding the
+    // bands each chunk touches, hi/lo halves interleaved along N (see MelTiles in seld_plan.h)
+    std::vector<uint16_t> bimg;
+    uint32_t mt_chunk[33] = {};
+    int mt_ok = (F == 513 && n_mels == 64);
+    if (mt_ok) {
+        auto bf16_rn = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); };
+        auto bf16_f = [](uint16_t h) { const uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; };
+        for (int c = 0; c < 33 && mt_ok; ++c) {
+            int lo = n_mels, hi = -1;
+            for (int k = 16 * c; k < 16 * c + 16 && k < F; ++k)
+                for (int m = 0; m < n_mels; ++m) {
+                    const float w = fb_host[(size_t)k * n_mels + m];
+                    if (!(fabsf(w) <= 3.0e38f)) mt_ok = 0;             // inf / nan weights: leave this form alone
+                    if (w != 0.0f) { if (m < lo) lo = m; if (m > hi) hi = m; }
+                }
+            int col0 = 0, n = 8;
+            if (hi >= 0) { col0 = lo & ~3; n = ((hi + 1 - col0) + 7) & ~7; if (col0 + n > n_mels) col0 = n_mels - n; }
+            if (c == 0) { col0 = 0; n = n_mels; }                      // first chunk: full width, overwrites the accumulator
+            const int N = 2 * n;
+            const size_t off = bimg.size();                            // in uint16
+            bimg.resize(off + (size_t)N * 16, 0);
+            for (int kk = 0; kk < 16; ++kk) {
+                const int k = 16 * c + kk;
+                for (int j = 0; j < n; ++j) {
+                    const float w = k < F ? fb_host[(size_t)k * n_mels + col0 + j] : 0.0f;
+                    const uint16_t h = bf16_rn(w), l = bf16_rn(w - bf16_f(h));
+                    for (int part = 0; part < 2; ++part) {
+                        const int nn = 2 * j + part;
+                        bimg[off + ((nn & 7) * 16 + (nn >> 3) * 256 + (kk & 7) * 2 + (kk >> 3) * 128) / 2] = part ? l : h;
+                    }
+                }
+            }
+            mt_chunk[c] = (uint32_t)(off * 2 / 16) | ((uint32_t)(2 * col0) << 16) | ((uint32_t)(N >> 3) << 24);
+        }
+        if (bimg.size() * 2 > 48 * 1024) mt_ok = 0;                    // dense banks: the tiles would not fit next to the rows
+    }
+    if (!mt_ok || bimg.empty()) bimg.assign(8, 0);
+
     seld_plan* p = new (std::nothrow) seld_plan();
     if (!p) return SELD_ENOMEM;
     memset(p, 0, sizeof(*p));
@@ -148,8 +190,8 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
 
     const size_t b_tw = tw.size() * 4, b_win = win.size() * 4, b_wt = wt.size() * 4, b_i = (size_t)n_mels_pad * 4;
     const size_t b_wab = wab.size() * 4, b_rm = 32 * 4, b_g0 = 32 * 4, b_gs = (size_t)gseg_pad * 4;
-    const size_t b_tw4 = tw4.size() * 4, b_win2 = win2.size() * 4;
-    const size_t total = b_tw + b_win + b_wt + 3 * b_i + b_wab + b_rm + b_g0 + b_gs + b_tw4 + b_win2;
+    const size_t b_tw4 = tw4.size() * 4, b_win2 = win2.size() * 4, b_bimg = bimg.size() * 2;
+    const size_t total = b_tw + b_win + b_wt + 3 * b_i + b_wab + b_rm + b_g0 + b_gs + b_tw4 + b_win2 + b_bimg + 16;
     e = cudaMalloc(&p->blob, total);
     if (e != cudaSuccess) { cudaSetDevice(prev); delete p; return cuda_fail(e); }
     std::vector<unsigned char> host(total, 0);
@@ -166,6 +208,8 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     memcpy(&host[o], gseg.data(), gseg.size() * 4); const size_t o_gs = o; o += b_gs;
     memcpy(&host[o], tw4.data(), b_tw4); const size_t o_tw4 = o; o += b_tw4;
     memcpy(&host[o], win2.data(), b_win2); const size_t o_win2 = o; o += b_win2;
+    o = (o + 15) & ~(size_t)15;                                        // the tile image is read as uint4
+    memcpy(&host[o], bimg.data(), b_bimg); const size_t o_bimg = o; o += b_bimg;
     e = cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { cudaFree(p->blob); delete p; return cuda_fail(e); }
@@ -183,6 +227,9 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     p->dev.runmask = (const uint32_t*)(d + o_rm);
     p->dev.g0 = (const int*)(d + o_g0);
     p->dev.gseg = (const int*)(d + o_gs);
+    p->mt.b_img = (const uint4*)(d + o_bimg);
+    p->mt.b_bytes = (int)b_bimg; p->mt.ok = mt_ok;
+    memcpy(p->mt.chunk, mt_chunk, sizeof(mt_chunk));
     p->dev.gseg_pad = gseg_pad;
     p->dev.fast_ok = fast_ok;
     p->dev.nnz_pad = (int)wt.size();
@@ -194,9 +241,19 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     if (seld::foa_smem_bytes(p->dev, span) > p->smem_optin) { seld_plan_destroy(p); return SELD_EUNSUPPORTED; }
     p->use_iv2 = false; p->iv_kernel = 0;
     {
-        const char* force = getenv("SELD_IV_KERNEL");      // experiments: 1 (general), 2, 3
-        const int want = force ? atoi(force) : 2;          // measured: iv2 (8 warps) 0.46 ms vs iv3 (16 warps) 0.52 ms at cfg2
-        if (want >= 3 && seld::foa_iv3_supported(p->dev, p->smem_optin)) p->iv_kernel = 3;
+        // Kernel choice is fixed here, once per plan (nothing reads the environment on the per-call path).
+        // SELD_IV_KERNEL is a developer switch for A/B runs: 1 = general kernel, 2 = fp32 mel walk (iv2, the default);
+        // builds with -DSELD_EXPERIMENTS also know 5 = tensor-core mel projection (iv5: measured 0.478 ms against
+        // 0.407 ms at cfg2) and 3 = two warps per frame (iv3).
+        const char* force = getenv("SELD_IV_KERNEL");
+        const int want = force ? atoi(force) : 2;
+        p->iv2_ok = seld::foa_iv2_supported(p->dev, p->smem_optin);
+        p->lm4_ok = want >= 2 && !getenv("SELD_NO_LM4") && seld::foa_iv2_supported(p->dev, p->smem_optin);
+        if (false) {}
+#ifdef SELD_EXPERIMENTS
+        else if (want == 5 && seld::foa_iv5_supported(p->dev, p->mt, p->smem_optin)) p->iv_kernel = 5;
+        else if (want == 3 && seld::foa_iv3_supported(p->dev, p->smem_optin)) p->iv_kernel = 3;
+#endif
         else if (want >= 2 && seld::foa_iv2_supported(p->dev, p->smem_optin)) p->iv_kernel = 2;
         p->use_iv2 = p->iv_kernel != 0;
     }
@@ -245,23 +302,38 @@ static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C,
     a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = out; a.L = L;
     a.B = (int)B; a.C = C; a.Cout = C + (iv ? 3 : 0); a.T = (int)T; a.c_lo = 0;
     a.span = 0; a.vec_ok = 0; a.in_i16 = i16 ? 1 : 0; a.in_scale = i16 ? 1.0f / 32768.0f : 1.0f;
-    if (i16 && !(iv && p->iv_kernel == 2 && C == 4)) return SELD_EUNSUPPORTED;   // PCM input: 4-channel iv2 path only
+    if (i16 && !(iv && (p->iv_kernel == 2 || p->iv_kernel == 5) && C == 4)) return SELD_EUNSUPPORTED;   // PCM input: fused 4-channel path only
     cudaStream_t st = (cudaStream_t)stream;
     bool general_iv = iv;
     if (iv && p->use_iv2) {
         // channels 0-3: log-mel + IV by the packed dual-FFT kernel; any further channels below
-        const int fpt = p->iv_kernel == 3 ? seld::foa_iv3_frames_per_tile() : seld::foa_iv2_frames_per_tile();
+        // iv5 stores 16-byte words: a misaligned output map goes to the fp32 mel walk instead
+        int kern = p->iv_kernel;
+        if (kern == 5 && ((uintptr_t)out & 15) != 0) {
+            if (!p->iv2_ok) return SELD_EUNSUPPORTED;
+            kern = 2;
+        }
+        int fpt = i16 ? 8 : seld::foa_iv2_frames_per_tile();          // PCM input always runs the 8-warp build
+#ifdef SELD_EXPERIMENTS
+        if (kern == 5) fpt = seld::foa_iv5_frames_per_tile();
+        if (kern == 3) fpt = seld::foa_iv3_frames_per_tile();
+#endif
         const int64_t tpc = (T + fpt - 1) / fpt;
         if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
         a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc);
-        cudaError_t e = p->iv_kernel == 3 ? seld::foa_iv3_launch(a, p->dev, p->sm_count, st)
-                                          : seld::foa_iv2_launch(a, p->dev, p->sm_count, st);
+        cudaError_t e;
+        if (false) {}
+#ifdef SELD_EXPERIMENTS
+        else if (kern == 5) e = seld::foa_iv5_launch(a, p->dev, p->mt, p->sm_count, st);
+        else if (kern == 3) e = seld::foa_iv3_launch(a, p->dev, p->sm_count, st);
+#endif
+        else e = seld::foa_iv2_launch(a, p->dev, p->sm_count, st);
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (C == 4) return SELD_OK;
         a.c_lo = 4; general_iv = false;
     }
-    if (!general_iv && p->iv_kernel == 2 && !i16 && !getenv("SELD_NO_LM4")) {
+    if (!general_iv && p->lm4_ok && !i16) {
         // log-mel of channels [c_lo, C): the packed dual-FFT kernel in its log-mel-only mode
         const int64_t jobs = T * (int64_t)(C - a.c_lo);
         const int jpt = seld::foa_lm4_jobs_per_tile();

@@ -20,6 +20,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "fft32.cuh"
 #include "seld_plan.h"
 
@@ -458,14 +460,19 @@ static size_t iv2_smem_bytes(const PlanDev& pd) {
 }
 
 // Warps (= frames) per block.  One block per SM; more warps hide latency, fewer leave more
-// registers per thread (8 -> 255, 12 -> 168; warps are allocated in fours).  SELD_IV2_WARPS overrides for experiments.
+// registers per thread (8 -> 255, 12 -> 168; warps are allocated in fours).  Measured at cfg2: 8 -> 0.46 ms,
+// 12 (spills) -> 0.51 ms; the 12-warp build only exists under -DSELD_EXPERIMENTS (SELD_IV2_WARPS=12).
 static int iv2_warps() {
+#ifdef SELD_EXPERIMENTS
     static int w = [] {
         const char* e = getenv("SELD_IV2_WARPS");
-        const int v = e ? atoi(e) : 8;                       // measured at cfg2: 8 -> 0.46 ms, 12 (spills) -> 0.51 ms
+        const int v = e ? atoi(e) : 8;
         return (v == 8 || v == 12) ? v : 8;
     }();
     return w;
+#else
+    return 8;
+#endif
 }
 
 bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin) {
@@ -477,8 +484,16 @@ int foa_iv2_frames_per_tile() { return iv2_warps(); }
 template <int W, typename TIn, bool kIV>
 static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
     const size_t smem = iv2_smem_bytes<W>(pd);
-    cudaError_t e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<uint64_t> attr_done{0};                              // per device, once per process and instantiation
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_relaxed) & bit)) {
+        e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done.fetch_or(bit, std::memory_order_relaxed);
+    }
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
     FoaArgs aa = a;
     aa.step_clip = gx / a.tiles_per_clip; aa.step_tile = gx - aa.step_clip * a.tiles_per_clip;
@@ -495,11 +510,11 @@ extern "C" void seld_dev_phase_cycles(unsigned long long* out, int reset) {
 #endif
 
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
-    if (a.in_i16) return iv2_launch_t<8, int16_t, true>(a, pd, sm_count, st);
-    switch (iv2_warps()) {
-        case 12: return iv2_launch_t<12, float, true>(a, pd, sm_count, st);
-        default: return iv2_launch_t<8, float, true>(a, pd, sm_count, st);
-    }
+    if (a.in_i16) return iv2_launch_t<8, int16_t, true>(a, pd, sm_count, st);   // PCM input: always the 8-warp build (frames_per_tile says 8 then, too)
+#ifdef SELD_EXPERIMENTS
+    if (iv2_warps() == 12) return iv2_launch_t<12, float, true>(a, pd, sm_count, st);
+#endif
+    return iv2_launch_t<8, float, true>(a, pd, sm_count, st);
 }
 
 // log-mel only, any channel count: channels [a.c_lo, a.C) of every clip; a.tiles_per_clip counts tiles of

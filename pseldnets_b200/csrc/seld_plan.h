@@ -31,6 +31,17 @@ struct PlanDev {
     float amin, eps;
 };
 
+// Mel bank as tensor-core B operand (iv5 kernel): 33 chunks of 16 bins.  Chunk c is a K-major, unswizzled bf16
+// tile [N_c columns x 16 bins] holding only the bands the chunk touches, hi and lo halves of each weight interleaved
+// along N (column 2j = hi of band col0_c + j, column 2j + 1 = lo), so one MMA per chunk lands in accumulator
+// columns [2 col0_c, 2 col0_c + N_c).  Chunk 0 is stored full width (N = 2 * 64): it overwrites the accumulator.
+struct MelTiles {
+    const uint4* b_img;      // device image of all tiles
+    int b_bytes;             // multiple of 16
+    int ok;                  // bank fits this form (n_mels == 64, tiles fit shared memory)
+    uint32_t chunk[33];      // tile offset in 16-byte units | first accumulator column << 16 | (N_c >> 3) << 24
+};
+
 struct FoaArgs {
     const void* x;           // (B, C, L) fp32 (or int16 PCM when in_i16), strides in elements
     float in_scale;          // 1 for fp32 input, 2^-15 for int16 PCM
@@ -56,6 +67,11 @@ int foa_iv2_frames_per_tile();
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
 int foa_lm4_jobs_per_tile();
 cudaError_t foa_lm4_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
+
+// tensor-core generation: fp32 transform + tcgen05 mel projection (seld_foa_iv5.cu)
+bool foa_iv5_supported(const PlanDev& pd, const MelTiles& mt, size_t smem_optin);
+int foa_iv5_frames_per_tile();
+cudaError_t foa_iv5_launch(const FoaArgs& a, const PlanDev& pd, const MelTiles& mt, int sm_count, cudaStream_t st);
 
 // third-generation kernel: two warps per frame (seld_foa_iv3.cu)
 bool foa_iv3_supported(const PlanDev& pd, size_t smem_optin);

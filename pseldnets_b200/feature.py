@@ -74,6 +74,19 @@ class _ExtractorBase(nn.Module):
         self.mel_scale = _Buffer('fb', self._make_bank())
         self._plans = {}
 
+    def __getstate__(self):
+        # Plans own raw device handles (ctypes pointers): they are per-process caches, rebuilt on first use.
+        # Keeping them out of the copied / pickled state is what makes copy.deepcopy(model), pickle and
+        # torch.save(model) work after a forward, as they do for the reference module (feature.py:20-37),
+        # and keeps two module copies from sharing (and double-freeing) one handle.
+        state = self.__dict__.copy()
+        state['_plans'] = {}
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._plans = {}
+
     def _make_bank(self):
         # MelScale(norm='slaney', f_min=20, f_max=sr/2, mel_scale='htk' default) -- feature.py:32-34
         return melscale_fbanks_htk_slaney(self.n_fft // 2 + 1, 20, self.sample_rate / 2, self.n_mels,
@@ -201,8 +214,9 @@ class LogmelGCC_Extractor(_ExtractorBase):
                          device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         top_db = -1.0 if self.top_db is None else float(self.top_db)
-        code = lib.seld_logmel_gcc_f32(plan.handle, x.data_ptr(), B, C, L, x.stride(0), x.stride(1), top_db,
-                                       out.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+        with _abi.device_guard(x.device):
+            code = lib.seld_logmel_gcc_f32(plan.handle, x.data_ptr(), B, C, L, x.stride(0), x.stride(1), top_db,
+                                           out.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
         _abi.check(code, self._entry)
         return out
 
