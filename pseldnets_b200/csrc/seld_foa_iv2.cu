@@ -47,6 +47,25 @@ constexpr int kTwStride = 68;             // 32 float2 + pad
 constexpr int kWinStride = 36;            // 32 floats + pad
 constexpr int kXStride = 34;              // exchange buffer row stride in float2 (even: 128-bit reads)
 constexpr int kWabStride = 36;            // floats per lane in the (a, b) weight table: 17 float2 + pad, 36*l mod 32 = 4l
+// Two real channels share each complex transform; splitting the packed spectrum leaves a channel with its partner's
+// rounding noise, about -120 dB relative to the PARTNER (measured: tests/test_imbalance_gpu.py).  A frame in which some
+// mel band of a channel lies that far under its partner's that the noise would show -- 50 dB for a log-mel row, 30 dB
+// for W (channel 0), whose relative error goes straight into the normalised intensity vector -- is noted in a
+// per-block list and transformed again at the end of the kernel with every channel alone in its transform (the
+// partner slot zero), which is exact down to digital silence.  Ordinary material never takes that path.
+// Mechanics: the main kernel marks such a frame by a sentinel (a NaN pattern no arithmetic produces) in element 0 of
+// one of its output rows; a second launch of the same kernel template in its kRedo form scans for sentinels and
+// recomputes those frames.  (A tail inside the main kernel was measured: it wrecks the register allocation of the
+// main loop, 0.73 ms instead of 0.41 ms.)  No state outside the output tensor, so calls on different streams do not
+// interact.
+// Band powers of stationary noise fluctuate (a narrow band is a chi-square with few degrees of freedom), so a single
+// band far under its partner's is no evidence of a level difference between channels: the loose thresholds only
+// count when three of eight neighbouring bands agree; one band alone must cross the strict threshold.
+constexpr float kTauRow = 1e-5f;          // loose: band power ratio under which a log-mel row would lose accuracy (50 dB)
+constexpr float kTauW = 2.5e-3f;          // loose, channel 0 of the IV kernel (26 dB: its relative error goes into every IV value)
+constexpr float kTauRowStrict = 1e-7f;    // strict (70 dB)
+constexpr float kTauWStrict = 1e-5f;      // strict, channel 0 of the IV kernel (50 dB)
+constexpr uint32_t kRedoMark = 0x7fc5e1d0u;   // quiet NaN with a payload
 
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -58,7 +77,7 @@ __device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.f
 // kIV = false: log-mel only (Logmel_Extractor, or channels >= 4 of a wider IV call).  The four transform
 //              slots of a warp then take four consecutive (frame, channel) jobs, j = t * Cj + c with
 //              Cj = C - c_lo channels, so any channel count keeps all four slots busy (C = 1: four frames).
-template <int W, typename TIn, bool kIV>
+template <int W, typename TIn, bool kIV, bool kRedo = false>
 __global__ void __launch_bounds__(W * 32, 1)
 foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,6 +90,41 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float in_scale = a.in_scale;
+    // redo form: groups of work (kIV: frames; log-mel only: groups of four (frame, channel) jobs, as in the main form)
+    // and the test for the main kernel's mark in element 0 of a group's output rows
+    const int redo_Cj = a.C - a.c_lo;
+    const int64_t redo_J = (int64_t)a.T * redo_Cj;                          // log-mel only: jobs per clip
+    const int64_t redo_gpc = kIV ? (int64_t)a.T : (redo_J + 3) / 4;         // groups per clip
+    const int64_t redo_groups = (int64_t)a.B * redo_gpc;
+    auto is_marked = [&](int64_t g) -> bool {
+        if (g >= redo_groups) return false;
+        const int b = (int)(g / redo_gpc), grp = (int)(g - (int64_t)b * redo_gpc);
+        const float* const o0 = a.out + ((int64_t)b * a.Cout) * ((int64_t)a.T * pd.n_mels);
+        if constexpr (kIV) {
+            return __float_as_uint(o0[((int64_t)a.C * a.T + grp) * pd.n_mels]) == kRedoMark;
+        } else {
+            bool marked = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t j = (int64_t)4 * grp + q;
+                if (j < redo_J)
+                    marked = marked || __float_as_uint(o0[((int64_t)(a.c_lo + (int)(j % redo_Cj)) * a.T + (j / redo_Cj)) * pd.n_mels]) == kRedoMark;
+            }
+            return marked;
+        }
+    };
+    if constexpr (!kRedo) {
+        // the redo scan is launched with programmatic stream serialisation: let it be scheduled while this grid runs
+        // (its blocks only become resident as ours retire, and wait for the whole grid before they read anything)
+        asm volatile("griddepcontrol.launch_dependents;");
+    }
+    if constexpr (kRedo) {                                                  // nothing marked (the normal case): leave before staging any table
+        asm volatile("griddepcontrol.wait;" ::: "memory");                  // the main grid has completed and its stores are visible
+        bool mine = false;
+        for (int64_t g0 = ((int64_t)blockIdx.x * W + warp) * 32; g0 < redo_groups; g0 += (int64_t)gridDim.x * W * 32)
+            mine = mine || is_marked(g0 + lane);
+        if (!__syncthreads_or(mine ? 1 : 0)) return;
+    }
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
         const float2 w = pd.tw[brev5(r) * 32 + l];
@@ -116,6 +170,164 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     long long phase_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long phase_t0 = clock64();
 #endif
+    // ---- mel projection of the rows a warp has just written (walk + combine + dB + store).  kCheck: also report whether
+    // some band of a slot lies too far under its partner's for the packed transform (the frame is then redone, see below)
+    auto mel_rows = [&](auto check_c, int b, int t, const int (&tk)[4], const int (&ck)[4], const bool (&vk)[4]) -> bool {
+        constexpr bool kCheck = decltype(check_c)::value;
+        bool bad = false;
+        PHASE_MARK(6);   // pointwise
+        // ---------------- mel step 1: chunk walk of all rows, per-run partial sums (U, V) left in the rows
+        constexpr int NR = kIV ? kRows : 4;
+        constexpr int NP = kIV ? kPairs : 2;                                // pair-rows in use
+        {
+            float2 wv[17];
+            const float4* wp = reinterpret_cast<const float4*>(wab_s + lane * kWabStride);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = wp[i];
+                wv[2 * i] = make_float2(v.x, v.y);
+                wv[2 * i + 1] = make_float2(v.z, v.w);
+            }
+            wv[16] = *reinterpret_cast<const float2*>(wab_s + lane * kWabStride + 32);
+            float2 q[NP][17];                                               // (row, row') values of the lane's 16 (+1) bins
+#pragma unroll
+            for (int f = 0; f < NP; ++f) {
+                const float* row = R + f * kPairWords;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + 32 * lane + 4 * (i ^ (lane & 7)));
+                    q[f][2 * i] = make_float2(v.x, v.y); q[f][2 * i + 1] = make_float2(v.z, v.w);
+                }
+                q[f][16] = lane == 31 ? *reinterpret_cast<const float2*>(row + 1024) : make_float2(0.0f, 0.0f);
+            }
+            __syncwarp();                                                   // everyone holds its bins: rows may be overwritten
+            PHASE_MARK(9);   // walk: weights + rows in registers
+            if (lane < NP) reinterpret_cast<float4*>(R + lane * kPairWords)[kZeroRun] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // per pair-row: U = sum a_k q_k and V = sum b_k q_k of the current run, each for both rows of the pair
+            float2 U[NP], V[NP];
+            float2* po = reinterpret_cast<float2*>(R) + 2 * g0;             // slot of run r: words 4r..4r+3 = (U, U', V, V'), two 64-bit stores
+                                                                            // (one 128-bit store would need the four values moved into an aligned register quad)
+            {
+                const float2 aa = make_float2(wv[0].x, wv[0].x), bb = make_float2(wv[0].y, wv[0].y);
+#pragma unroll
+                for (int f = 0; f < NP; ++f) { U[f] = __fmul2_rn(aa, q[f][0]); V[f] = __fmul2_rn(bb, q[f][0]); }
+            }
+            // branch-free: where a new run starts the finished sums are stored and the accumulators restart
+            // (acc * keep with keep = 0); the weights are broadcast once per bin for all rows
+            static_for<1, 17>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const bool start = (runmask >> j) & 1u;
+                const float keep = start ? 0.0f : 1.0f;
+                const float2 kk = make_float2(keep, keep);
+                const float2 aa = make_float2(wv[j].x, wv[j].x), bb = make_float2(wv[j].y, wv[j].y);
+#pragma unroll
+                for (int f = 0; f < NP; ++f) {
+                    if (start) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
+                    U[f] = __ffma2_rn(aa, q[f][j], __fmul2_rn(U[f], kk));
+                    V[f] = __ffma2_rn(bb, q[f][j], __fmul2_rn(V[f], kk));
+                }
+                po += start ? 2 : 0;
+            });
+#pragma unroll
+            for (int f = 0; f < NP; ++f) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
+        }
+        __syncwarp();
+
+        PHASE_MARK(7);   // mel walk
+        // ---------------- mel step 2: band per lane, out[m] = sum V(runs of segment m) + sum U(runs of segment m+1)
+        {
+            // destination of row f (one 64-float line of the output per row): kIV: channels 0-3 and the three
+            // IV channels of frame t; log-mel only: (channel, frame) of slot f, if that slot holds a job
+            float* const ob = a.out + ((int64_t)b * a.Cout) * ch_stride + (kIV ? (int64_t)t * M : 0);
+            auto emit = [&](int f, int m, float v) {
+                if (f < 4) v = 3.01029995663981195f * lg2_ftz(fmaxf(v, amin));   // 10*log10(max(v, amin))
+                if constexpr (kIV) {
+                    ob[(f < 4 ? f : a.C + f - 4) * ch_stride + m] = v;
+                } else {
+                    if (vk[f & 3]) ob[ck[f & 3] * ch_stride + (int64_t)tk[f & 3] * M + m] = v;
+                }
+            };
+            // imbalance check (see kTauRow / kTauW): rows 0..3 are the powers of the four transform slots, partners (0,1), (2,3)
+            auto unbalanced = [](const float (&v)[NR], float t0, float t) {
+                return v[0] < t0 * v[1] || v[1] < t * v[0] || v[2] < t * v[3] || v[3] < t * v[2];
+            };
+            // some aligned group of eight bands (a byte of the ballot) with three or more bits set
+            auto clustered = [](uint32_t m) {
+                uint32_t c = m - ((m >> 1) & 0x55555555u);
+                c = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);
+                c = (c + (c >> 4)) & 0x0f0f0f0fu;
+                return ((c + 0x05050505u) & 0x08080808u) != 0u;
+            };
+            if (M <= 64) {
+                // fixed slots: <= 4 runs per segment, run numbers held packed in registers (absent -> the zero run);
+                // all loads are issued up front (a data-dependent slot count was measured 2.4 % slower)
+                auto combine = [&](auto four_c) {
+                    constexpr bool kFour = decltype(four_c)::value;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int m = lane + 32 * r;
+                        bool loose = false;
+                        if (m < M) {
+                            const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
+                            float2 vv[NP];                                  // both rows of a pair per packed add
+#pragma unroll
+                            for (int f = 0; f < NP; ++f) {
+                                const float2* rowp = reinterpret_cast<const float2*>(R + f * kPairWords);   // slot r: [2r] = U pair, [2r+1] = V pair
+                                const float2 v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
+                                const float2 v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
+                                const float2 u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
+                                const float2 u2 = rowp[2 * ((pu >> 16) & 0xff)];
+                                if constexpr (kFour) {
+                                    const float2 v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
+                                    vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, v3)), vadd(vadd(u0, u1), vadd(u2, u3)));
+                                } else {
+                                    vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
+                                }
+                            }
+                            float v[NR];
+                            v[0] = vv[0].x; v[2] = vv[0].y; v[1] = vv[1].x; v[3] = vv[1].y;
+                            if constexpr (kIV) { v[4] = vv[2].x; v[6] = vv[2].y; v[5] = vv[3].x; }
+                            if constexpr (kCheck) {
+                                bad = bad || unbalanced(v, kIV ? kTauWStrict : kTauRowStrict, kTauRowStrict);
+                                loose = unbalanced(v, kIV ? kTauW : kTauRow, kTauRow);
+                            }
+#pragma unroll
+                            for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
+                        }
+                        if constexpr (kCheck) {
+                            const uint32_t lm = __ballot_sync(0xffffffffu, loose);   // every lane votes (no short-circuit in front of it)
+                            bad = clustered(lm) || bad;
+                        }
+                    }
+                };
+                if (four) combine(std::true_type{}); else combine(std::false_type{});
+            } else {
+                const float4* P = reinterpret_cast<const float4*>(R);        // slot g of pair-row f: (U, U', V, V')
+                for (int m = lane; m < M; m += 32) {
+                    const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
+                    float2 vv[NP];
+#pragma unroll
+                    for (int f = 0; f < NP; ++f) vv[f] = make_float2(0.0f, 0.0f);
+                    for (int g = ga; g < gb; ++g) {
+#pragma unroll
+                        for (int f = 0; f < NP; ++f) { const float4 t = P[f * (kPairWords / 4) + g]; vv[f] = vadd(vv[f], make_float2(t.z, t.w)); }
+                    }
+                    for (int g = gb; g < gc; ++g) {
+#pragma unroll
+                        for (int f = 0; f < NP; ++f) { const float4 t = P[f * (kPairWords / 4) + g]; vv[f] = vadd(vv[f], make_float2(t.x, t.y)); }
+                    }
+                    float v[NR];
+                    v[0] = vv[0].x; v[2] = vv[0].y; v[1] = vv[1].x; v[3] = vv[1].y;
+                    if constexpr (kIV) { v[4] = vv[2].x; v[6] = vv[2].y; v[5] = vv[3].x; }
+                    if constexpr (kCheck) bad = bad || unbalanced(v, kIV ? kTauW : kTauRow, kTauRow);   // wide banks: any band
+#pragma unroll
+                    for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
+                }
+            }
+        }
+        return bad;
+    };
+
     // tile = (clip tb, tile tr within the clip), advanced by the grid size without a division per frame (the
     // division was a 500-cycle dependent chain at the top of every frame)
     int tb = blockIdx.x / a.tiles_per_clip, tr = blockIdx.x - tb * a.tiles_per_clip;
@@ -123,6 +335,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         tb += a.step_clip; tr += a.step_tile;
         if (tr >= a.tiles_per_clip) { tr -= a.tiles_per_clip; ++tb; }
     };
+    if constexpr (!kRedo) {
     for (; tb < a.B; next_tile()) {
         const int b = tb;
         const int grp = tr * W + warp;                                      // kIV: the frame; else: group of 4 jobs
@@ -299,154 +512,157 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         }
         __syncwarp();
 
-        PHASE_MARK(6);   // pointwise
-        // ---------------- mel step 1: chunk walk of all rows, per-run partial sums (U, V) left in the rows
-        constexpr int NR = kIV ? kRows : 4;
-        constexpr int NP = kIV ? kPairs : 2;                                // pair-rows in use
-        {
-            float2 wv[17];
-            const float4* wp = reinterpret_cast<const float4*>(wab_s + lane * kWabStride);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v = wp[i];
-                wv[2 * i] = make_float2(v.x, v.y);
-                wv[2 * i + 1] = make_float2(v.z, v.w);
-            }
-            wv[16] = *reinterpret_cast<const float2*>(wab_s + lane * kWabStride + 32);
-            float2 q[NP][17];                                               // (row, row') values of the lane's 16 (+1) bins
-#pragma unroll
-            for (int f = 0; f < NP; ++f) {
-                const float* row = R + f * kPairWords;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(row + 32 * lane + 4 * (i ^ (lane & 7)));
-                    q[f][2 * i] = make_float2(v.x, v.y); q[f][2 * i + 1] = make_float2(v.z, v.w);
-                }
-                q[f][16] = lane == 31 ? *reinterpret_cast<const float2*>(row + 1024) : make_float2(0.0f, 0.0f);
-            }
-            __syncwarp();                                                   // everyone holds its bins: rows may be overwritten
-            PHASE_MARK(9);   // walk: weights + rows in registers
-            if (lane < NP) reinterpret_cast<float4*>(R + lane * kPairWords)[kZeroRun] = make_float4(0.f, 0.f, 0.f, 0.f);
-            // per pair-row: U = sum a_k q_k and V = sum b_k q_k of the current run, each for both rows of the pair
-            float2 U[NP], V[NP];
-            float2* po = reinterpret_cast<float2*>(R) + 2 * g0;             // slot of run r: words 4r..4r+3 = (U, U', V, V'), two 64-bit stores
-                                                                            // (one 128-bit store would need the four values moved into an aligned register quad)
-            {
-                const float2 aa = make_float2(wv[0].x, wv[0].x), bb = make_float2(wv[0].y, wv[0].y);
-#pragma unroll
-                for (int f = 0; f < NP; ++f) { U[f] = __fmul2_rn(aa, q[f][0]); V[f] = __fmul2_rn(bb, q[f][0]); }
-            }
-            // branch-free: where a new run starts the finished sums are stored and the accumulators restart
-            // (acc * keep with keep = 0); the weights are broadcast once per bin for all rows
-            static_for<1, 17>([&](auto ji) {
-                constexpr int j = decltype(ji)::value;
-                const bool start = (runmask >> j) & 1u;
-                const float keep = start ? 0.0f : 1.0f;
-                const float2 kk = make_float2(keep, keep);
-                const float2 aa = make_float2(wv[j].x, wv[j].x), bb = make_float2(wv[j].y, wv[j].y);
-#pragma unroll
-                for (int f = 0; f < NP; ++f) {
-                    if (start) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
-                    U[f] = __ffma2_rn(aa, q[f][j], __fmul2_rn(U[f], kk));
-                    V[f] = __ffma2_rn(bb, q[f][j], __fmul2_rn(V[f], kk));
-                }
-                po += start ? 2 : 0;
-            });
-#pragma unroll
-            for (int f = 0; f < NP; ++f) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
-        }
-        __syncwarp();
-
-        PHASE_MARK(7);   // mel walk
-        // ---------------- mel step 2: band per lane, out[m] = sum V(runs of segment m) + sum U(runs of segment m+1)
-        {
-            // destination of row f (one 64-float line of the output per row): kIV: channels 0-3 and the three
-            // IV channels of frame t; log-mel only: (channel, frame) of slot f, if that slot holds a job
-            float* const ob = a.out + ((int64_t)b * a.Cout) * ch_stride + (kIV ? (int64_t)t * M : 0);
-            auto emit = [&](int f, int m, float v) {
-                if (f < 4) v = 3.01029995663981195f * lg2_ftz(fmaxf(v, amin));   // 10*log10(max(v, amin))
-                if constexpr (kIV) {
-                    ob[(f < 4 ? f : a.C + f - 4) * ch_stride + m] = v;
-                } else {
-                    if (vk[f & 3]) ob[ck[f & 3] * ch_stride + (int64_t)tk[f & 3] * M + m] = v;
-                }
-            };
-            // Channels 0/1 and 2/3 share a packed transform; a digitally silent one comes out of the untangle step as
-            // its partner's rounding noise (<= -130 dB relative) instead of exact zeros.  For log-mel that hides under
-            // the amin clamp unless the partner is loud, but the normalised intensity vector turns a noise-only I_j
-            // into +-1 when nothing else is there to normalise against (W-only input, or a silent W).  The reference
-            // gives exact zeros in those cases; so a band whose mel power is more than 120 dB under its partner's --
-            // below what the packed fp32 transform resolves -- is set to zero, with the IV rows that depend on it.
-            auto silence_unresolved = [](float (&v)[NR]) {
-                if constexpr (NR == 7) {
-                    constexpr float kRel = 1e-12f;
-                    const bool d0 = v[0] < kRel * v[1], d1 = v[1] < kRel * v[0];
-                    const bool d2 = v[2] < kRel * v[3], d3 = v[3] < kRel * v[2];
-                    v[0] = d0 ? 0.0f : v[0]; v[1] = d1 ? 0.0f : v[1]; v[2] = d2 ? 0.0f : v[2]; v[3] = d3 ? 0.0f : v[3];
-                    v[4] = (d0 || d1) ? 0.0f : v[4]; v[5] = (d0 || d2) ? 0.0f : v[5]; v[6] = (d0 || d3) ? 0.0f : v[6];
-                }
-            };
-            if (M <= 64) {
-                // fixed slots: <= 4 runs per segment, run numbers held packed in registers (absent -> the zero run);
-                // all loads are issued up front (a data-dependent slot count was measured 2.4 % slower)
-                auto combine = [&](auto four_c) {
-                    constexpr bool kFour = decltype(four_c)::value;
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const int m = lane + 32 * r;
-                        if (m < M) {
-                            const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
-                            float2 vv[NP];                                  // both rows of a pair per packed add
-#pragma unroll
-                            for (int f = 0; f < NP; ++f) {
-                                const float2* rowp = reinterpret_cast<const float2*>(R + f * kPairWords);   // slot r: [2r] = U pair, [2r+1] = V pair
-                                const float2 v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
-                                const float2 v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
-                                const float2 u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
-                                const float2 u2 = rowp[2 * ((pu >> 16) & 0xff)];
-                                if constexpr (kFour) {
-                                    const float2 v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
-                                    vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, v3)), vadd(vadd(u0, u1), vadd(u2, u3)));
-                                } else {
-                                    vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
-                                }
-                            }
-                            float v[NR];
-                            v[0] = vv[0].x; v[2] = vv[0].y; v[1] = vv[1].x; v[3] = vv[1].y;
-                            if constexpr (kIV) { v[4] = vv[2].x; v[6] = vv[2].y; v[5] = vv[3].x; }
-                            if constexpr (kIV) silence_unresolved(v);
-#pragma unroll
-                            for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
-                        }
-                    }
-                };
-                if (four) combine(std::true_type{}); else combine(std::false_type{});
+        const bool bad = mel_rows(std::true_type{}, b, t, tk, ck, vk);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) {                    // lane 0 also wrote element 0 of every row: program order
+            float* const o0 = a.out + ((int64_t)b * a.Cout) * ch_stride;
+            if constexpr (kIV) {
+                o0[(int64_t)a.C * ch_stride + (int64_t)t * M] = __uint_as_float(kRedoMark);
             } else {
-                const float4* P = reinterpret_cast<const float4*>(R);        // slot g of pair-row f: (U, U', V, V')
-                for (int m = lane; m < M; m += 32) {
-                    const int ga = gseg_s[m], gb = gseg_s[m + 1], gc = gseg_s[m + 2];
-                    float2 vv[NP];
 #pragma unroll
-                    for (int f = 0; f < NP; ++f) vv[f] = make_float2(0.0f, 0.0f);
-                    for (int g = ga; g < gb; ++g) {
-#pragma unroll
-                        for (int f = 0; f < NP; ++f) { const float4 t = P[f * (kPairWords / 4) + g]; vv[f] = vadd(vv[f], make_float2(t.z, t.w)); }
-                    }
-                    for (int g = gb; g < gc; ++g) {
-#pragma unroll
-                        for (int f = 0; f < NP; ++f) { const float4 t = P[f * (kPairWords / 4) + g]; vv[f] = vadd(vv[f], make_float2(t.x, t.y)); }
-                    }
-                    float v[NR];
-                    v[0] = vv[0].x; v[2] = vv[0].y; v[1] = vv[1].x; v[3] = vv[1].y;
-                    if constexpr (kIV) { v[4] = vv[2].x; v[6] = vv[2].y; v[5] = vv[3].x; }
-                    if constexpr (kIV) silence_unresolved(v);
-#pragma unroll
-                    for (int f = 0; f < NR; ++f) emit(f, m, v[f]);
-                }
+                for (int q = 0; q < 4; ++q)
+                    if (vk[q]) o0[(int64_t)ck[q] * ch_stride + (int64_t)tk[q] * M] = __uint_as_float(kRedoMark);
             }
         }
         __syncwarp();                                                       // rows are reused by the next frame's exchange
         PHASE_MARK(8);   // mel combine + store
+    }
+
+    } else {
+    // ---------------- frames whose channels were too unbalanced for the packed transform: once more, every slot alone
+    // in its transform (pass 0: slots 0 and 2, pass 1: slots 1 and 3; the partner slot is zero, so nothing leaks and a
+    // silent channel comes out as exact zeros, like the reference's one-FFT-per-channel, feature.py:49)
+    {
+        const int Cj = redo_Cj;
+        const int64_t J = redo_J, gpc = redo_gpc;
+        auto redo = [&](int b, int grp) {
+            int tk[4] = {grp, grp, grp, grp}, ck[4] = {0, 1, 2, 3};
+            bool vk[4] = {true, true, true, true};
+            if constexpr (!kIV) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t j = (int64_t)4 * grp + q;
+                    vk[q] = j < J;
+                    tk[q] = vk[q] ? (int)(j / Cj) : 0;
+                    ck[q] = a.c_lo + (vk[q] ? (int)(j % Cj) : 0);
+                }
+            }
+            const TIn* xb = reinterpret_cast<const TIn*>(a.x) + (int64_t)b * a.stride_b;
+            float x0r[17], x0i[17], i2s[17];                                  // kIV: W spectrum and Re(conj(X0) X2) of pass 0
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                float2 re[32], im[32];
+                const int ta = tk[pass], tb2 = tk[pass + 2];
+                const bool va = vk[pass], vb = vk[pass + 2];
+                const TIn* pa = xb + (int64_t)ck[pass] * a.stride_c;
+                const TIn* pb = xb + (int64_t)ck[pass + 2] * a.stride_c;
+                auto sample = [&](const TIn* p, bool valid, int tt, int m) -> float {
+                    if (!valid) return 0.0f;
+                    int64_t sidx = (int64_t)tt * hop - 512 + 32 * m + lane;
+                    if (sidx < 0) sidx = -sidx;
+                    if (sidx >= a.L) sidx = 2 * (a.L - 1) - sidx;
+                    return (float)__ldg(p + sidx);
+                };
+                static_for<0, 32>([&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    re[m] = make_float2(sample(pa, va, ta, m), sample(pb, vb, tb2, m));
+                    im[m] = make_float2(0.0f, 0.0f);
+                });
+                static_for<0, 8>([&](auto mi) {
+                    constexpr int m4 = decltype(mi)::value;
+                    const float4 w4 = *reinterpret_cast<const float4*>(win_s + lane * kWinStride + 4 * m4);
+                    const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) re[4 * m4 + e] = vmuls(re[4 * m4 + e], w[e]);
+                });
+                fft32(re, im);
+                static_for<0, 16>([&](auto pi) {
+                    constexpr int p2 = decltype(pi)::value;
+                    const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
+                    if constexpr (p2 > 0) {
+                        const float2 r = re[2 * p2], i = im[2 * p2];
+                        re[2 * p2] = vfmas(i, -w4.y, vmuls(r, w4.x));
+                        im[2 * p2] = vfmas(i, w4.x, vmuls(r, w4.y));
+                    }
+                    const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
+                    re[2 * p2 + 1] = vfmas(i, -w4.w, vmuls(r, w4.z));
+                    im[2 * p2 + 1] = vfmas(i, w4.z, vmuls(r, w4.w));
+                });
+                __syncwarp();
+                // exchange behind pair-row 0 (which holds pass 0's powers during pass 1): floats [1056, 3232) of the region
+                float2* xs = scratch + kPairWords / 2;
+                static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; xs[brev5(p) * kXStride + lane] = re[p]; });
+                __syncwarp();
+                static_for<0, 16>([&](auto ji) {
+                    constexpr int j = decltype(ji)::value;
+                    const float4 v = *reinterpret_cast<const float4*>(xs + lane * kXStride + 2 * j);
+                    re[2 * j] = make_float2(v.x, v.y); re[2 * j + 1] = make_float2(v.z, v.w);
+                });
+                __syncwarp();
+                static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; xs[brev5(p) * kXStride + lane] = im[p]; });
+                __syncwarp();
+                static_for<0, 16>([&](auto ji) {
+                    constexpr int j = decltype(ji)::value;
+                    const float4 v = *reinterpret_cast<const float4*>(xs + lane * kXStride + 2 * j);
+                    im[2 * j] = make_float2(v.x, v.y); im[2 * j + 1] = make_float2(v.z, v.w);
+                });
+                __syncwarp();
+                fft32(re, im);
+                const int src = (32 - lane) & 31;
+                const bool lane0 = lane == 0;
+                static_for<0, 17>([&](auto kbi) {
+                    constexpr int kb = decltype(kbi)::value;
+                    constexpr int p = brev5(kb & 31);
+                    const float2 zr = re[p], zi = im[p];
+                    float2 pr, pi;
+                    if constexpr (kb == 16) {
+                        pr = zr; pi = zi;
+                    } else {
+                        constexpr int pp = brev5(31 - kb), p0 = brev5((32 - kb) & 31);
+                        const float sx = __shfl_sync(0xffffffffu, re[pp].x, src), sy = __shfl_sync(0xffffffffu, re[pp].y, src);
+                        const float tx = __shfl_sync(0xffffffffu, im[pp].x, src), ty = __shfl_sync(0xffffffffu, im[pp].y, src);
+                        pr = make_float2(lane0 ? re[p0].x : sx, lane0 ? re[p0].y : sy);
+                        pi = make_float2(lane0 ? im[p0].x : tx, lane0 ? im[p0].y : ty);
+                    }
+                    const float2 ar = vadd(zr, pr), ai = vsub(zi, pi);      // spectra of the two live slots (the other two are zero)
+                    const float2 pw = __ffma2_rn(ai, ai, __fmul2_rn(ar, ar));
+                    const bool wr = kb < 16 || lane == 0;
+                    float2* q = reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
+                    if (wr) q[pass * (kPairWords / 2)] = pw;               // pass 0: (P0, P2), pass 1: (P1, P3)
+                    if constexpr (kIV) {
+                        if (pass == 0) {
+                            x0r[kb] = ar.x; x0i[kb] = ai.x;
+                            i2s[kb] = fmaf(ai.x, ai.y, ar.x * ar.y);       // Re(conj(X0) X2)
+                        } else {
+                            const float2 i13 = vfmas(ai, x0i[kb], vmuls(ar, x0r[kb]));   // Re(conj(X0) X1), Re(conj(X0) X3)
+                            const float i2 = i2s[kb];
+                            const float sq = fmaf(i13.y, i13.y, fmaf(i2, i2, i13.x * i13.x));
+                            const float inv = rcp_ftz(sqrt_ftz(sq) + eps);
+                            if (wr) {
+                                q[2 * (kPairWords / 2)] = vmuls(i13, inv);
+                                q[3 * (kPairWords / 2)] = make_float2(i2 * inv, 0.0f);
+                            }
+                        }
+                    }
+                });
+                __syncwarp();
+            }
+            mel_rows(std::false_type{}, b, tk[0], tk, ck, vk);
+            __syncwarp();
+        };
+        // scan: a warp looks at 32 groups at a time (one per lane), then redoes the marked ones
+        const int64_t wid = (int64_t)blockIdx.x * W + warp, nw = (int64_t)gridDim.x * W;
+        for (int64_t g0 = wid * 32; g0 < redo_groups; g0 += nw * 32) {
+            const bool marked = is_marked(g0 + lane);
+            uint32_t todo = __ballot_sync(0xffffffffu, marked);
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t gg = g0 + l;
+                const int b = (int)(gg / gpc);
+                redo(b, (int)(gg - (int64_t)b * gpc));
+            }
+        }
+    }
     }
 #ifdef SELD_PHASE_TIMING
     if (lane == 0) for (int i = 0; i < 10; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)phase_acc[i]);
@@ -492,13 +708,28 @@ static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_coun
     if (!(attr_done.load(std::memory_order_relaxed) & bit)) {
         e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
         attr_done.fetch_or(bit, std::memory_order_relaxed);
     }
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
     FoaArgs aa = a;
     aa.step_clip = gx / a.tiles_per_clip; aa.step_tile = gx - aa.step_clip * a.tiles_per_clip;
     foa_iv2_kernel<W, TIn, kIV><<<gx, W * 32, smem, st>>>(aa, pd);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // second launch: frames the main kernel marked as too unbalanced for the packed transform (normally none: the
+    // kernel then only scans one output element per frame)
+    const int64_t groups = (int64_t)a.B * (kIV ? (int64_t)a.T : ((int64_t)a.T * (a.C - a.c_lo) + 3) / 4);
+    const int64_t blocks = (groups + 32 * W - 1) / (32 * W);
+    const int gr = (int)(blocks < sm_count ? blocks : sm_count);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)gr); cfg.blockDim = dim3(W * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, foa_iv2_kernel<W, TIn, kIV, true>, aa, pd);
 }
 
 #ifdef SELD_PHASE_TIMING

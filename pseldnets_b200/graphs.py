@@ -50,6 +50,19 @@ class GraphedFrontEnd:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = self._run()
+        # The recorded kernel nodes hold pointers into the plan's device tables: keep that plan alive for as long as
+        # the graph exists, and remember which buffer contents it was built from.
+        self._plan = extractor._plan(dev)
+        self._plan_key = self._buffers_key()
+
+    def _buffers_key(self):
+        win, fb = self.extractor.stft_extractor.window, self.extractor.mel_scale.fb
+        return (win.data_ptr(), win._version, fb.data_ptr(), fb._version)
+
+    def _check_buffers(self):
+        if self._buffers_key() != self._plan_key:
+            raise RuntimeError('the extractor\'s window / mel bank changed after the graph was recorded '
+                               '(load_state_dict, .to(), in-place edit): record a new GraphedFrontEnd')
 
     def _run(self):
         y = self.extractor(self.static_in)
@@ -62,6 +75,7 @@ class GraphedFrontEnd:
     def replay(self):
         """Replay on whatever `static_in` holds (fill it directly, e.g. as the target of the host->device copy,
         to skip the staging copy of __call__); returns the static output buffer."""
+        self._check_buffers()
         self.graph.replay()
         return self.static_out
 
@@ -69,6 +83,7 @@ class GraphedFrontEnd:
         if tuple(x.shape) != self.shape or x.dtype != self.static_in.dtype:
             raise ValueError('GraphedFrontEnd was recorded for %s %s, got %s %s'
                              % (self.shape, self.static_in.dtype, tuple(x.shape), x.dtype))
+        self._check_buffers()
         self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.static_out.clone() if clone else self.static_out

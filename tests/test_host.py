@@ -286,3 +286,38 @@ def test_paired_row_layout_of_the_iv2_kernel():
         for phase in range(4):
             groups = {((32 * lane + 4 * (i ^ (lane & 7))) % 32) // 4 for lane in range(8 * phase, 8 * phase + 8)}
             assert len(groups) == 8
+
+
+def test_extractor_survives_copy_and_pickle_with_live_plans():
+    """The reference extractor is a plain nn.Module: copy.deepcopy / pickle / torch.save of a model that owns it
+    work at any time (feature.py:20-37; tests/golden/make_golden.py deep-copies it).  The drop-in caches device
+    plans holding raw ctypes handles after its first forward; those must stay out of the copied state, and two
+    copies must never share (and double-free) one handle."""
+    import copy
+    import io
+    import pickle
+
+    class FakePlan:                      # stands in for feature._Plan after a forward: an unpicklable ctypes handle
+        def __init__(self):
+            self.handle = ctypes.c_void_p(0xdead0000)
+
+    for cls, feat in ((pb.LogmelIV_Extractor, 'logmelIV'), (pb.Logmel_Extractor, 'logmel'),
+                      (pb.LogmelGCC_Extractor, 'logmelgcc')):
+        ext = cls(make_cfg(feat=feat))
+        ext._plans[0] = (('key',), FakePlan())
+        with pytest.raises(Exception):
+            pickle.dumps(ext._plans)                       # the cache itself is not picklable: that was the bug
+        for clone in (copy.deepcopy(ext), copy.copy(ext), pickle.loads(pickle.dumps(ext))):
+            assert clone._plans == {} and clone._plans is not ext._plans
+            assert torch.equal(clone.stft_extractor.window, ext.stft_extractor.window)
+            assert torch.equal(clone.mel_scale.fb, ext.mel_scale.fb)
+            assert clone.n_fft == ext.n_fft and clone.hop == ext.hop
+        assert len(ext._plans) == 1                        # the original keeps its plan
+        holder = torch.nn.Sequential(ext)                  # as a sub-module of a model (af_extractor)
+        buf = io.BytesIO()
+        torch.save(holder, buf)
+        buf.seek(0)
+        back = torch.load(buf, weights_only=False)
+        assert back[0]._plans == {}
+        assert sorted(back.state_dict().keys()) == sorted(holder.state_dict().keys())
+        ext._plans.clear()
