@@ -134,3 +134,49 @@ def test_epilogue_oracle_fold_semantics():
     assert img[1, 0, 2, 3] == x[1, 0, 3, 2]                  # piece 0: row m, column t
     assert img[0, 0, 4 + 1, 1] == x[0, 0, 8 + 1, 1]          # piece 1 sits below piece 0
     assert not img[:, :, 4:, 2:].any()                       # frames 10..15 are zero padding
+
+
+def _mic_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'mic.npz'))
+
+
+def test_mic_bank_against_torchaudio_slaney():
+    """`librosa.filters.mel` restated (filterbank.librosa_mel_bank, feature.py:126) against torchaudio's independent
+    Slaney-scale / Slaney-norm bank stored in tests/golden/mic.npz."""
+    g = _mic_golden()
+    for sr in (24000, 32000):
+        ours = fbk.librosa_mel_bank(sr, 1024, 64).numpy()
+        ref = g['bank_%d' % sr]
+        assert ours.shape == ref.shape == (513, 64)
+        assert np.abs(ours - ref).max() <= 1e-7 * 1.0 and np.abs(ours - ref).max() / np.abs(ref).max() <= 5e-6
+        assert np.array_equal(ours != 0, ref != 0) or np.abs(ours[(ours != 0) != (ref != 0)]).max() < 1e-7
+
+
+def test_mic_oracle_is_pinned_to_the_independent_evaluation():
+    """The MIC oracle (numpy restatement of feature.py:146-175 + preprocess.py:546-556) against vectors produced by a
+    different library stack (torch.stft / torchaudio bank / torch.fft.irfft: tests/golden/make_golden_mic.py) on
+    eight seeded inputs: white, full scale, pure delays, 120 dB quiet tail (top_db floor), zero-filled tail, dead
+    microphone, 32 kHz, ragged length.  fp64 oracle: log-mel 1e-5 of the block maximum, GCC 1e-6 absolute; fp32 oracle:
+    the north_star tolerances."""
+    g = _mic_golden()
+    for name in g['names']:
+        sr, hop = (int(v) for v in g[name + '/sr_hop'])
+        x, y64 = g[name + '/x'], g[name + '/y64']
+        w = fbk.make_window('hann', 1024).numpy()
+        bank = fbk.librosa_mel_bank(sr, 1024, 64).numpy()
+        sz = set(int(p) for p in g[name + '/signed_zero_planes'])
+        ok = [4 + p for p in range(6) if p not in sz]
+        for dtype, tol_lm, tol_gcc in ((np.float64, 1e-5, 1e-6), (np.float32, 1e-4, 1e-4)):
+            y = so.logmel_gcc(x, w, bank, 1024, hop, dtype=dtype)
+            assert y.shape == y64.shape, name
+            assert block_err(y, y64, slice(0, 4)) <= tol_lm, (name, dtype)
+            assert np.abs(y[:, ok].astype(np.float64) - y64[:, ok]).max() <= tol_gcc, (name, dtype)
+        # without the top_db floor (power_to_db(top_db=None))
+        y = so.logmel_gcc(x, w, bank, 1024, hop, top_db=None, dtype=np.float64)
+        assert block_err(y[:, :4], g[name + '/y64_notopdb'], slice(0, 4)) <= 1e-5, name
+        if sz:
+            # digitally silent microphone: the cross-spectrum is an exact zero whose SIGN pattern decides angle() --
+            # numpy and torch do not agree with each other there (the reference is implementation-defined)
+            bad = [4 + p for p in sorted(sz)]
+            y = so.logmel_gcc(x, w, bank, 1024, hop, dtype=np.float64)
+            assert np.abs(y[:, bad] - y64[:, bad]).max() > 1e-2
