@@ -87,6 +87,19 @@ int seld_logmel_gcc_f32(const seld_plan* plan, const float* x, int64_t B, int C,
                         int64_t stride_b, int64_t stride_c, float top_db, float* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same path in the reference's three stages, for callers that drive them separately as
+ * Preprocess.extract_mic_features does (preprocess.py:546-556):
+ * seld_mic_spectrogram_f32           Features_Extractor_MIC._spectrogram (feature.py:146-153): x (B, C=4, L) ->
+ *                                    spec (B, T, n_fft/2+1, C) complex64 (interleaved re, im; 16-byte aligned),
+ *                                    i.e. the reference's (T, F, C) array per clip, T = L / hop;
+ * seld_logmel_gcc_from_spectra_f32   _get_logmel_spectrogram + _get_gcc (feature.py:155-175) of such an array ->
+ *                                    out (B, 4 + 6, T, n_mels) as seld_logmel_gcc_f32 lays it out. */
+int seld_mic_spectrogram_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,
+                             int64_t stride_b, int64_t stride_c, float* spec, void* stream);
+int seld_logmel_gcc_from_spectra_f32(const seld_plan* plan, const float* spec, int64_t B, int C, int64_t T,
+                                     float top_db, float* out, void* workspace, size_t workspace_bytes,
+                                     void* stream);
+
 /* ---- Backbone-input stage: what every backbone does first with the feature map.
  *
  * seld_scalar_f32: the per-channel eval-mode BatchNorm2d "scalar" loop of the backbones

@@ -36,6 +36,11 @@ SIGNATURES = {
     'seld_logmel_gcc_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64, _i64, _i64,
                                            ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                            ctypes.c_void_p]),
+    'seld_mic_spectrogram_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64, _i64, _i64,
+                                                ctypes.c_void_p, ctypes.c_void_p]),
+    'seld_logmel_gcc_from_spectra_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _i64, ctypes.c_int, _i64,
+                                                        ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                        ctypes.c_void_p]),
     'seld_scalar_f32': (ctypes.c_int, [ctypes.c_void_p, _i64, ctypes.c_int, _i64, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
                                        ctypes.c_void_p]),

@@ -488,6 +488,54 @@ extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B
     return SELD_OK;
 }
 
+extern "C" int seld_mic_spectrogram_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,
+                                        int64_t stride_b, int64_t stride_c, float* spec, void* stream) {
+    if (!p || B < 0 || C < 1 || L < 1) return SELD_EINVAL;
+    if (C != 4) return SELD_EUNSUPPORTED;
+    if (!seld::mic_supported(p->dev, p->smem_optin)) return SELD_EUNSUPPORTED;
+    const int64_t T = L / p->dev.hop;
+    if (B == 0 || T == 0) return SELD_OK;
+    if (!x || !spec) return SELD_EINVAL;
+    if ((uintptr_t)spec & 15) return SELD_EUNSUPPORTED;
+    if (T > INT32_MAX) return SELD_EUNSUPPORTED;
+    const int fpt = seld::mic_frames_per_tile();
+    const int64_t tpc = (T + fpt - 1) / fpt;
+    if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
+    seld::FoaArgs a{};
+    a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.out = nullptr; a.L = L; a.spec = spec;
+    a.B = (int)B; a.C = C; a.Cout = C + C * (C - 1) / 2; a.T = (int)T; a.c_lo = 0;
+    a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.in_scale = 1.0f;
+    cudaError_t e = seld::mic_spectrogram_launch(a, p->dev, p->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
+extern "C" int seld_logmel_gcc_from_spectra_f32(const seld_plan* p, const float* spec, int64_t B, int C, int64_t T,
+                                                float top_db, float* out, void* workspace, size_t workspace_bytes,
+                                                void* stream) {
+    if (!p || B < 0 || C < 1 || T < 0) return SELD_EINVAL;
+    if (C != 4) return SELD_EUNSUPPORTED;
+    if (!seld::mic_supported(p->dev, p->smem_optin)) return SELD_EUNSUPPORTED;
+    if (B == 0 || T == 0) return SELD_OK;
+    if (!spec || !out || !workspace) return SELD_EINVAL;
+    if ((uintptr_t)spec & 15) return SELD_EUNSUPPORTED;
+    if (workspace_bytes < seld_workspace_bytes(p, B, C)) return SELD_EINVAL;
+    if (T > INT32_MAX) return SELD_EUNSUPPORTED;
+    const int fpt = seld::mic_frames_per_tile();
+    const int64_t tpc = (T + fpt - 1) / fpt;
+    if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
+    seld::FoaArgs a{};
+    a.x = nullptr; a.out = out; a.L = T * p->dev.hop; a.spec = const_cast<float*>(spec);
+    a.B = (int)B; a.C = C; a.Cout = C + C * (C - 1) / 2; a.T = (int)T; a.c_lo = 0;
+    a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.in_scale = 1.0f;
+    const bool use_top_db = top_db >= 0.0f;
+    cudaError_t e = seld::mic_launch(a, p->dev, (int*)workspace, top_db, use_top_db, p->sm_count, (cudaStream_t)stream, true);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(use_top_db ? 2 : 1, std::memory_order_relaxed);
+    return SELD_OK;
+}
+
 // ---- backbone-input stage (stateless: no plan)
 static int current_sm_count(int* sm) {
     static std::atomic<int> cache[64];

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "fft32.cuh"
 #include "mel_seg.cuh"
 #include "seld_plan.h"
@@ -59,6 +61,12 @@ __device__ __forceinline__ float2 cross_phasor(float2 ua, float2 ub) {
 }
 }  // namespace mic
 
+// kMode 0: waveform -> features (the fused path).
+// kMode 1: waveform -> complex spectrogram only (Features_Extractor_MIC._spectrogram, feature.py:146-153): a.spec receives
+//          (B, T, 513, 4) complex64, i.e. the reference's (T, F, C) layout per clip.
+// kMode 2: features from a given spectrogram in that layout (_get_logmel_spectrogram / _get_gcc, feature.py:155-175):
+//          the forward transform is skipped, everything after it is the same code.
+template <int kMode>
 __global__ void __launch_bounds__(mic::kW * 32, 1)
 mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey) {
     using namespace mic;
@@ -108,7 +116,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     int cur_b = -1;
     float rmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     auto flush_max = [&]() {
-        if (cur_b < 0) return;
+        if (kMode == 1 || cur_b < 0) return;                               // spectrogram mode: no dB planes, no maxima
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float v = rmax[c];
@@ -128,6 +136,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         const int64_t s0 = (int64_t)t * hop - 512;
 
         float2 re[32], im[32];
+        float* const spec_g = static_cast<float*>(a.spec) + (((int64_t)b * a.T + t) * 513) * 8;   // kMode 1 / 2: this frame's (513, 4) complex block
+        if constexpr (kMode != 2) {
         // ---------------- load + window: re = (mic0, mic2), im = (mic1, mic3); zeros outside the clip
         if (s0 >= 0 && s0 + 1024 <= a.L) {
             const float* p0 = xb + s0 + lane;
@@ -191,26 +201,46 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         });
         __syncwarp();
         fft32(re, im);
+        }  // kMode != 2
 
         // ---------------- untangle: spectra -> spec[c][k], powers -> rows
         float min_n = 1.0f;                                                 // becomes 0 if any channel has a vanishing bin
         static_for<0, 17>([&](auto kbi) {
             constexpr int kb = decltype(kbi)::value;
             constexpr int p = brev5(kb & 31);
-            const float2 zr = re[p], zi = im[p];
-            float2 pr, pi;
-            if constexpr (kb == 16) {
-                pr = zr; pi = zi;
+            float2 ar, ai, br, bi;                                          // (X0, X2) and (X1, X3), real and imaginary parts
+            if constexpr (kMode == 2) {
+                float4 c01 = make_float4(0.f, 0.f, 0.f, 0.f), c23 = c01;
+                if (kb < 16 || lane == 0) {
+                    const float4* g4 = reinterpret_cast<const float4*>(spec_g + (int64_t)(lane + 32 * kb) * 8);
+                    c01 = __ldg(g4); c23 = __ldg(g4 + 1);
+                }
+                ar = make_float2(c01.x, c23.x); ai = make_float2(c01.y, c23.y);
+                br = make_float2(c01.z, c23.z); bi = make_float2(c01.w, c23.w);
             } else {
-                constexpr int pp = brev5(31 - kb), p0 = brev5((32 - kb) & 31);
-                pr.x = __shfl_sync(0xffffffffu, re[pp].x, src);
-                pr.y = __shfl_sync(0xffffffffu, re[pp].y, src);
-                pi.x = __shfl_sync(0xffffffffu, im[pp].x, src);
-                pi.y = __shfl_sync(0xffffffffu, im[pp].y, src);
-                if (lane == 0) { pr = re[p0]; pi = im[p0]; }
+                const float2 zr = re[p], zi = im[p];
+                float2 pr, pi;
+                if constexpr (kb == 16) {
+                    pr = zr; pi = zi;
+                } else {
+                    constexpr int pp = brev5(31 - kb), p0 = brev5((32 - kb) & 31);
+                    pr.x = __shfl_sync(0xffffffffu, re[pp].x, src);
+                    pr.y = __shfl_sync(0xffffffffu, re[pp].y, src);
+                    pi.x = __shfl_sync(0xffffffffu, im[pp].x, src);
+                    pi.y = __shfl_sync(0xffffffffu, im[pp].y, src);
+                    if (lane == 0) { pr = re[p0]; pi = im[p0]; }
+                }
+                ar = vadd(zr, pr); ai = vsub(zi, pi);
+                br = vadd(zi, pi); bi = vsub(pr, zr);
             }
-            const float2 ar = vadd(zr, pr), ai = vsub(zi, pi);              // (X0, X2)
-            const float2 br = vadd(zi, pi), bi = vsub(pr, zr);              // (X1, X3)
+            if constexpr (kMode == 1) {
+                if (kb < 16 || lane == 0) {
+                    float4* g4 = reinterpret_cast<float4*>(spec_g + (int64_t)(lane + 32 * kb) * 8);
+                    g4[0] = make_float4(ar.x, ai.x, br.x, bi.x);
+                    g4[1] = make_float4(ar.y, ai.y, br.y, bi.y);
+                }
+                return;
+            }
             const float2 p02 = __ffma2_rn(ai, ai, __fmul2_rn(ar, ar));
             const float2 p13 = __ffma2_rn(bi, bi, __fmul2_rn(br, br));
             if (kb < 16 || lane == 0) {
@@ -232,6 +262,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             }
         });
         __syncwarp();
+        if constexpr (kMode == 1) continue;
 
         // ---------------- log-mel of the four power rows (unclamped dB + running maximum)
         float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
@@ -468,15 +499,41 @@ bool mic_supported(const PlanDev& pd, size_t smem_optin) {
 
 int mic_frames_per_tile() { return mic::kW; }
 
+template <int kMode>
+static cudaError_t mic_set_attr() {
+    static std::atomic<uint64_t> done{0};                                   // per device, once per process and instantiation
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_relaxed) & bit)) {
+        e = cudaFuncSetAttribute(mic_features_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        done.fetch_or(bit, std::memory_order_relaxed);
+    }
+    return cudaSuccess;
+}
+
+// waveform -> (B, T, 513, 4) complex64 spectrogram in a.spec
+cudaError_t mic_spectrogram_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
+    cudaError_t e = mic_set_attr<1>();
+    if (e != cudaSuccess) return e;
+    const int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
+    mic_features_kernel<1><<<gx, mic::kW * 32, mic_smem_bytes(pd), st>>>(a, pd, nullptr);
+    return cudaGetLastError();
+}
+
+// from_spectra: a.spec holds the (B, T, 513, 4) complex64 spectrogram, a.x is unused
 cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float top_db, bool use_top_db,
-                       int sm_count, cudaStream_t st) {
+                       int sm_count, cudaStream_t st, bool from_spectra) {
     const size_t smem = mic_smem_bytes(pd);
-    cudaError_t e = cudaFuncSetAttribute(mic_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = from_spectra ? mic_set_attr<2>() : mic_set_attr<0>();
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(maxkey, 0x80, (size_t)a.B * 4 * sizeof(int), st);  // key 0x80808080: below any dB value
     if (e != cudaSuccess) return e;
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
-    mic_features_kernel<<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
+    if (from_spectra) mic_features_kernel<2><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
+    else mic_features_kernel<0><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
     e = cudaGetLastError();
     if (e != cudaSuccess || !use_top_db) return e;
     const int64_t plane = (int64_t)a.T * pd.n_mels;                         // multiple of 4 (n_mels = 64)

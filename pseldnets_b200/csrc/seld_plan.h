@@ -53,6 +53,7 @@ struct FoaArgs {
     int c_lo;                // first input channel this launch covers (log-mel of channels c_lo..C-1)
     int tiles_per_clip, n_tiles;
     int step_clip, step_tile;  // iv2: grid size split as step_clip * tiles_per_clip + step_tile (set by the launcher)
+    void* spec;              // MIC only: (B, T, 513, 4) complex64 spectrogram, written (spectrogram mode) or read (from-spectra mode)
     int span;                // staged samples per channel per tile (multiple of 4)
     int vec_ok;              // x base/strides allow 16-byte loads
 };
@@ -83,7 +84,8 @@ cudaError_t foa_iv3_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cu
 bool mic_supported(const PlanDev& pd, size_t smem_optin);
 int mic_frames_per_tile();
 cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float top_db, bool use_top_db,
-                       int sm_count, cudaStream_t st);
+                       int sm_count, cudaStream_t st, bool from_spectra = false);
+cudaError_t mic_spectrogram_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st);
 
 // backbone-input stage (seld_epilogue.cu): eval-mode BatchNorm "scalar" terms, each (C, M) on the device;
 // mean == nullptr means "no scalar" (identity)

@@ -222,11 +222,19 @@ class LogmelGCC_Extractor(_ExtractorBase):
 
 
 class Features_Extractor_MIC():
-    """Name-compatible front for the reference's MIC class (feature.py:119-175).  The fused kernel
-    never materialises the complex spectrogram, so instead of the three numpy stages
-    (_spectrogram -> _get_logmel_spectrogram / _get_gcc) it exposes their composition as used by
-    Preprocess.extract_mic_features (preprocess.py:546-556): (L, C) float32 audio in soundfile
-    layout -> (C + C(C-1)/2, T, n_mels) float32 numpy feature."""
+    """Drop-in for the reference's MIC class (feature.py:119-175) with its three stages, so that
+    Preprocess.extract_mic_features (preprocess.py:546-556) runs against it unchanged:
+
+        spect  = ext._spectrogram(waveform, nb_frames)        # (T, n_fft/2+1, C) complex64
+        logmel = ext._get_logmel_spectrogram(spect)           # (T, n_mels, C)
+        gcc    = ext._get_gcc(spect)                          # (T, n_mels, C(C-1)/2)
+
+    Each stage is one CUDA launch (seld_mic_spectrogram_f32 / seld_logmel_gcc_from_spectra_f32); the two feature
+    stages share one launch when they are given the same spectrogram array.  `extract_logmelgcc(waveform)` is the
+    fused path (one launch, the spectrogram never leaves the SM) and returns preprocess.py's final
+    (C + C(C-1)/2, T, n_mels) float32 array directly.  `mel_bank` is `librosa.filters.mel(...).T` as in the
+    reference.  SALSA-Lite (`_get_salsalite`) is outside this path (it crashes in the reference on numpy >= 1.24).
+    """
 
     def __init__(self, cfg, device='cuda'):
         self.fs = cfg['data']['sample_rate']
@@ -236,6 +244,62 @@ class Features_Extractor_MIC():
         self.window = cfg['data']['window']
         self._ext = LogmelGCC_Extractor(cfg).to(device)
         self.mel_bank = self._ext.mel_scale.fb.cpu().numpy()
+        self._last = None                      # (spectrogram array, features) of the latest from-spectra launch
+
+    def _device(self):
+        dev = self._ext.mel_scale.fb.device
+        return dev if dev.index is not None else torch.device('cuda', torch.cuda.current_device())
+
+    def _spectrogram(self, audio_input, _nb_frames):
+        """(L, C) float waveform in soundfile layout -> (min(_nb_frames, L // hop), n_fft/2+1, C) complex64"""
+        import numpy as np
+        ext, dev = self._ext, self._device()
+        x = torch.as_tensor(np.ascontiguousarray(np.asarray(audio_input, dtype=np.float32).T)).to(dev)   # (C, L)
+        C, L = x.shape
+        T = L // ext.hop
+        spec = torch.empty((1, T, ext.n_fft // 2 + 1, C), dtype=torch.complex64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with _abi.device_guard(dev):
+            code = _abi.lib().seld_mic_spectrogram_f32(ext._plan(dev).handle, x.data_ptr(), 1, C, L, C * L, L,
+                                                       spec.data_ptr(), stream)
+        _abi.check(code, 'seld_mic_spectrogram_f32')
+        return spec[0, :_nb_frames].cpu().numpy()
+
+    def _features_from_spectra(self, linear_spectra):
+        import numpy as np
+        if self._last is not None and self._last[0] is linear_spectra:
+            return self._last[1]
+        ext, dev = self._ext, self._device()
+        sp = np.ascontiguousarray(np.asarray(linear_spectra, dtype=np.complex64))
+        if sp.ndim != 3 or sp.shape[1] != ext.n_fft // 2 + 1:
+            raise ValueError('linear_spectra must be (n_frames, n_fft/2+1, n_channels), got %s' % (sp.shape,))
+        T, _, C = sp.shape
+        spec = torch.from_numpy(sp).to(dev)
+        out = torch.empty((1, C + C * (C - 1) // 2, T, ext.n_mels), dtype=torch.float32, device=dev)
+        lib = _abi.lib()
+        plan = ext._plan(dev)
+        ws = torch.empty((max(1, lib.seld_workspace_bytes(plan.handle, 1, C) // 4),), dtype=torch.int32, device=dev)
+        top_db = -1.0 if ext.top_db is None else float(ext.top_db)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with _abi.device_guard(dev):
+            code = lib.seld_logmel_gcc_from_spectra_f32(plan.handle, spec.data_ptr(), 1, C, T, top_db, out.data_ptr(),
+                                                        ws.data_ptr(), ws.numel() * 4, stream)
+        _abi.check(code, 'seld_logmel_gcc_from_spectra_f32')
+        feat = out[0].cpu().numpy()
+        self._last = (linear_spectra, feat)
+        return feat
+
+    def _get_logmel_spectrogram(self, linear_spectra):
+        """(T, F, C) complex -> (T, n_mels, C) float64 container, as the reference's np.zeros(...) gives"""
+        import numpy as np
+        C = linear_spectra.shape[-1]
+        return np.ascontiguousarray(self._features_from_spectra(linear_spectra)[:C].transpose(1, 2, 0)).astype(np.float64)
+
+    def _get_gcc(self, linear_spectra):
+        """(T, F, C) complex -> (T, n_mels, C(C-1)/2) float64 container"""
+        import numpy as np
+        C = linear_spectra.shape[-1]
+        return np.ascontiguousarray(self._features_from_spectra(linear_spectra)[C:].transpose(1, 2, 0)).astype(np.float64)
 
     def extract_logmelgcc(self, waveform):
         x = torch.as_tensor(waveform, dtype=torch.float32).t().unsqueeze(0)        # (1, C, L)

@@ -189,3 +189,41 @@ def test_mic_cfg3_full_size():
     assert (y3[:, 4:] - y[:2, 4:]).abs().max().item() < 1e-4
     assert (y3[:, :4] - y[:2, :4] - 20.0 * np.log10(3.0)).abs().max().item() < 1e-4 * y[:2, :4].abs().max().item()
     _check(y[:2].cpu().numpy(), _oracle(ext, x[:2].cpu().numpy()), 'cfg3 clips 0-1')
+
+
+def test_mic_reference_stage_methods_run_preprocess_unchanged():
+    """Features_Extractor_MIC with the reference's three stages: the body of Preprocess.extract_mic_features
+    (preprocess.py:546-556) runs against the drop-in verbatim and yields the fixture features; the spectrogram has
+    the reference's layout and values ((T, 513, C) complex64: torch.stft with zero centre padding)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'mic.npz'))
+    for name in ('white_24k', 'delay_24k', 'quiet_tail_24k', 'ragged_24k', 'white_32k'):
+        sr, hop = (int(v) for v in g[name + '/sr_hop'])
+        af_extractor_mic = pb.Features_Extractor_MIC(make_cfg(sr, hop, 'hann', 'logmelgcc'))
+        hoplen = hop
+        for b in range(g[name + '/x'].shape[0]):
+            waveform = np.ascontiguousarray(g[name + '/x'][b].T)                 # sf.read layout: (L, C) float32
+            # ---- preprocess.py:546-556, unchanged
+            nb_feat_frams = int(len(waveform) / hoplen)
+            spect = af_extractor_mic._spectrogram(waveform, nb_feat_frams)
+            logmel_spec = af_extractor_mic._get_logmel_spectrogram(spect)
+            gcc = af_extractor_mic._get_gcc(spect)
+            feature = np.concatenate((logmel_spec, gcc), axis=-1).transpose((2, 0, 1))
+            # ----
+            assert spect.shape == (nb_feat_frams, 513, 4) and spect.dtype == np.complex64
+            assert logmel_spec.shape == (nb_feat_frams, 64, 4) and gcc.shape == (nb_feat_frams, 64, 6)
+            _check(feature[None].astype(np.float32), g[name + '/y64'][b:b + 1], name + ' via the three stages')
+            fused = af_extractor_mic.extract_logmelgcc(waveform)
+            _check(fused[None], g[name + '/y64'][b:b + 1], name + ' fused')
+            # the spectrogram itself against torch.stft (fp64)
+            xt = torch.from_numpy(g[name + '/x'][b]).double()
+            X = torch.stft(xt, 1024, hop, 1024, torch.hann_window(1024, dtype=torch.float64), center=True,
+                           pad_mode='constant', return_complex=True)[..., :nb_feat_frams].permute(2, 1, 0).numpy()
+            assert np.abs(spect - X).max() <= 2e-6 * np.abs(X).max(), name
+    # a spectrogram that did not come from _spectrogram (any array of that layout works), and fewer frames than available
+    front = pb.Features_Extractor_MIC(make_cfg(24000, 240, 'hann', 'logmelgcc'))
+    wav = np.ascontiguousarray(g['white_24k/x'][0].T)
+    sp = front._spectrogram(wav, 9)
+    assert sp.shape == (9, 513, 4)
+    lm = front._get_logmel_spectrogram(sp.copy())
+    assert lm.shape == (9, 64, 4) and np.isfinite(lm).all()
