@@ -147,59 +147,98 @@ def library_ops_same_gpu(x, window, fb):
     return torch.cat((logmel, iv), dim=1)
 
 
-def cpu_port_throughput(batch, min_seconds, max_calls, threads):
-    """The reference's CPU path (oracle/torch_port.py: same torch.stft / matmul calls as the
-    reference makes through torchaudio) on the host cores.  Returns (audio-s/s, calls, seconds)."""
+def cpu_reference_callable():
+    """The reference's CPU implementation of the path as a callable x (B, 4, L) -> features, and what it is:
+    'reference' = the UNMODIFIED /root/reference/src/utils/feature.py, vendored by __graft_entry__.build() into the
+    git-ignored baseline/_ref/ (it travels to the GPU box with the snapshot; only `librosa`, which the FOA extractor
+    never touches, is stubbed); 'port' = oracle/torch_port.py (the same torch.stft / matmul calls, pinned to the
+    reference's goldens) when that file is not there."""
     import torch
+    path = os.path.join(ROOT, 'baseline', '_ref', 'utils', 'feature.py')
+    if os.path.exists(path):
+        try:
+            import importlib.util
+            import types
+            sys.modules.setdefault('librosa', types.ModuleType('librosa'))
+            spec = importlib.util.spec_from_file_location('pseldnets_reference_feature', path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            ext = mod.LogmelIV_Extractor(CFG).eval()
+
+            def call(x):
+                with torch.no_grad():
+                    return ext(x)
+            return call, 'reference', 'unmodified reference feature.py (LogmelIV_Extractor, torchaudio) from baseline/_ref, torch CPU fp32'
+        except Exception as e:                                   # e.g. torchaudio missing on the box
+            sys.stderr.write('reference module unusable (%s); timing the torch port\n' % (e,))
     from oracle import torch_port
     from pseldnets_b200 import filterbank as fbk
-    torch.set_num_threads(threads)
     win = fbk.make_window('hann', NFFT)
     fb = fbk.melscale_fbanks_htk_slaney(NFFT // 2 + 1, 20, SR / 2, NMELS, SR)
+    return (lambda x: torch_port.logmel_iv(x, win, fb, NFFT, HOP)), 'port', 'torch CPU fp32 port of feature.py (oracle/torch_port.py)'
+
+
+def cpu_baseline_throughput(batch, min_seconds, max_calls, threads):
+    """The reference's CPU path on the host cores, bounded sample.  Returns (audio-s/s, calls, seconds, kind, what)."""
+    import torch
+    torch.set_num_threads(threads)
+    call, kind, what = cpu_reference_callable()
     g = torch.Generator().manual_seed(1234)
     x = 0.1 * torch.randn(batch, C, L, generator=g)
-    torch_port.logmel_iv(x, win, fb, NFFT, HOP)          # warm-up
+    call(x)                                                # warm-up
     times = []
     t_start = time.perf_counter()
     while len(times) < max_calls and (time.perf_counter() - t_start < min_seconds or len(times) < 3):
         t0 = time.perf_counter()
-        torch_port.logmel_iv(x, win, fb, NFFT, HOP)
+        call(x)
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return batch * CLIP_S / med, len(times), sum(times)
+    return batch * CLIP_S / med, len(times), sum(times), kind, what
+
+
+def cfg2_config(B, world):
+    return {'workload': 'cfg2: FOA log-mel+IV, batch %d x 10 s x 4 ch @ 24 kHz per GPU -> (%d,7,1001,64)' % (B, B),
+            'n_fft': NFFT, 'hop': HOP, 'n_mels': NMELS, 'per_gpu_batch': B, 'global_batch': B * world,
+            'sharding': 'by clip, no collective on the data path',
+            'l2': 'inputs 245.8 MB + outputs 114.8 MB per step exceed the 126 MB L2 (no flush needed)'}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (torch port of
-    feature.py -- the Python reference tree cannot travel to the GPU box), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (the unmodified
+    feature.py from baseline/_ref when present, else the torch port), all host threads, on OUR arm's config: every
+    step is one call on the full 64-clip batch.  Rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     import torch
-    from oracle import torch_port
-    from pseldnets_b200 import filterbank as fbk
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sample_b = 8                                           # bounded sample of the 64-clip batch
-    win = fbk.make_window('hann', NFFT)
-    fb = fbk.melscale_fbanks_htk_slaney(NFFT // 2 + 1, 20, SR / 2, NMELS, SR)
+    call, kind, what = cpu_reference_callable()
+    B = args.batch
     g = torch.Generator().manual_seed(1234)
-    x = 0.1 * torch.randn(sample_b, C, L, generator=g)
+    x = 0.1 * torch.randn(B, C, L, generator=g)
     for _ in range(args.warmup):
-        torch_port.logmel_iv(x, win, fb, NFFT, HOP)
+        call(x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        torch_port.logmel_iv(x, win, fb, NFFT, HOP)
+        call(x)
     dt = time.perf_counter() - t0
-    value = args.steps * sample_b * CLIP_S / dt
-    sample = '%d of 64 clips per step (10 s, 4 ch, 24 kHz), torch CPU fp32' % sample_b
-    # SURVEY 8d cfg1: the same on ONE host thread, one clip (B = 1), median of 5 after 2 warm-ups; and the host CPU
+    value = args.steps * B * CLIP_S / dt
+    # the same on an 8-clip sample (large CPU batches are allocator-bound: the smaller call is the reference's better case)
+    x8 = x[:8].contiguous()
+    call(x8)
+    t8 = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        call(x8)
+        t8.append(time.perf_counter() - t0)
+    # SURVEY 8d cfg1: ONE host thread, one clip (B = 1), median of 5 after 2 warm-ups; and the host CPU
     torch.set_num_threads(1)
-    x1 = x[:1]
+    x1 = x[:1].contiguous()
     t1 = []
     for i in range(7):
         t0 = time.perf_counter()
-        torch_port.logmel_iv(x1, win, fb, NFFT, HOP)
+        call(x1)
         if i >= 2:
             t1.append(time.perf_counter() - t0)
     torch.set_num_threads(threads)
@@ -211,36 +250,30 @@ def run_reference(args):
                 break
     except OSError:
         pass
+    sample = 'every step = one call on the full batch of %d clips (10 s, 4 ch, 24 kHz); %s' % (B, what)
     emit_json(({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'cfg2 FOA log-mel+IV, 10 s x 4 ch @ 24 kHz clips; CPU sample of %d clips/step' % sample_b,
-                   'n_fft': NFFT, 'hop': HOP, 'n_mels': NMELS},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'config': cfg2_config(B, 1),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'sample_8_clips': {'value': 8 * CLIP_S / statistics.median(t8), 'unit': UNIT, 'cores': threads,
+                           'sample': 'calls of 8 clips, median of 5'},
         'cfg1_one_thread': {'value': CLIP_S / statistics.median(t1), 'unit': UNIT, 'ms_per_clip': 1e3 * statistics.median(t1),
                             'cores': 1, 'sample': 'one 10-s clip (B = 1), median of 5'},
         'host_cpu': cpu_model,
     }))
 
 
-def run_extra(args):
-    """cfg3 / cfg4 of BASELINE.json: resident-input throughput + roofline of the extra workloads."""
+def extra_record(workload, steps, warmup, dev, rank, world, dist=None):
+    """cfg3 / cfg4 of BASELINE.json on this rank's GPU: resident-input time per step, roofline fraction and the SM
+    clocks sampled DURING its own timed region.  Returns the record on rank 0 (None elsewhere)."""
     import torch
-    import torch.distributed as dist
     import pseldnets_b200 as pb
     from pseldnets_b200 import _abi, shard
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
-    if args.workload == 'cfg3':
+    if workload == 'cfg3':
         sr, hop, Lw, Cin, name = 24000, 240, 240000, 4, 'cfg3: MIC log-mel+GCC-PHAT, batch 64 x 10 s x 4 mics @ 24 kHz per GPU -> (64,10,1000,64)'
         ext = pb.get_afextractor({'data': dict(CFG['data'], audio_feature='logmelgcc')}).to(dev)
         nb = 64
@@ -258,49 +291,51 @@ def run_extra(args):
         scaling = 'strong'
     g = torch.Generator(device=dev).manual_seed(1235 + rank)
     x = 0.1 * torch.randn(nb, Cin, Lw, device=dev, generator=g)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         y = step(x)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.01)
+        sampler.mark()
     l0 = _abi.lib().seld_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         y = step(x)
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0]) / args.steps
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        n_global = nb * world if args.workload == 'cfg3' else 128
-        algo = nb * (Cin * Lw * 4 + out_bytes)
-        emit_json(({'metric': 'audio-seconds/sec (%s)' % args.workload, 'value': n_global * CLIP_S / (ms * 1e-3), 'unit': UNIT,
-                          'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
-                          'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                          'config': {'workload': name},
-                          'roofline': {'bound': 'hbm', 'achieved': algo / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                                       'frac': algo / (ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
-                                       'algorithmic_bytes_per_step_per_gpu': algo},
-                          'gpu_launches': int(_abi.lib().seld_launch_count() - l0), 'outputs_finite': bool(torch.isfinite(y).all())}))
-    if world > 1:
-        dist.destroy_process_group()
+    ms = float(t[0]) / steps
+    finite = bool(torch.isfinite(y).all())
+    del x, y
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    n_global = nb * world if workload == 'cfg3' else 128
+    algo = nb * (Cin * Lw * 4 + out_bytes)
+    return {'metric': 'audio-seconds/sec (%s)' % workload, 'value': n_global * CLIP_S / (ms * 1e-3), 'unit': UNIT,
+            'n_gpus': world, 'steps': steps, 'warmup': max(warmup, 3), 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': name},
+            'roofline': {'bound': 'hbm', 'achieved': algo / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': algo / (ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_step_per_gpu': algo},
+            'gpu_launches': int(_abi.lib().seld_launch_count() - l0), 'clocks': clocks, 'outputs_finite': finite}
 
 
-def run_epoch(args):
-    """cfg5 of BASELINE.json / SURVEY 8d: one epoch sweep of the reference's training set -- 67,000 one-minute clips
-    = 402,000 ten-second chunks (configs/data/default.yaml:15-21; chunked before extraction, preprocess.py:464-521)
-    -- sharded by chunk over the ranks, batches of 64 from a resident pool of 4 synthetic batches per rank (984 MB,
-    cycled; generation excluded from the time).  Time = max over ranks for the whole sweep."""
+def run_extra(args):
+    """--workload cfg3 / cfg4: the extra workloads of BASELINE.json as their own JSON line (any N)."""
     import torch
     import torch.distributed as dist
-    import pseldnets_b200 as pb
-    from pseldnets_b200 import _abi, shard
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -309,9 +344,43 @@ def run_epoch(args):
     if world > 1:
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
-    n_chunks = 402000
+    rec = extra_record(args.workload, args.steps, args.warmup, dev, rank, world, dist)
+    if rank == 0:
+        emit_json(rec)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_epoch(args):
+    """--workload cfg5: the whole epoch sweep as its own JSON line (any N)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=dev)
+    rec = epoch_record(402000, args.batch, dev, rank, world, dist)
+    if rank == 0:
+        emit_json(rec)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def epoch_record(n_chunks, B, dev, rank, world, dist=None):
+    """cfg5 of BASELINE.json / SURVEY 8d: one epoch sweep of the reference's training set -- 67,000 one-minute clips
+    = 402,000 ten-second chunks (configs/data/default.yaml:15-21; chunked before extraction, preprocess.py:464-521)
+    -- sharded by chunk over the ranks, batches of 64 from a resident pool of 4 synthetic batches per rank (984 MB,
+    cycled; generation excluded from the time).  Time = max over ranks for the whole sweep.  `n_chunks` < 402,000 is
+    the SCALED sweep the default bench line carries (same code path, a fixed fraction of the epoch)."""
+    import torch
+    import pseldnets_b200 as pb
+    from pseldnets_b200 import _abi, shard
+    local_rank = dev.index or 0
     lo, hi = shard.clip_shard(n_chunks, rank, world)
-    B = args.batch
     n_local = hi - lo
     steps = (n_local + B - 1) // B
     ext = pb.get_afextractor(CFG).to(dev)
@@ -350,24 +419,26 @@ def run_epoch(args):
         finite = bool(torch.isfinite(table).all())
     else:
         finite = bool(torch.isfinite(first[0]).all())
-    if rank == 0:
-        sec = float(t[0]) * 1e-3
-        peak, peak_src = measured_peaks()
-        algo = n_chunks * ALGO_BYTES_PER_CLIP
-        emit_json(({
-            'metric': 'audio-seconds/sec (cfg5 epoch sweep)', 'value': n_chunks * CLIP_S / sec, 'unit': UNIT, 'n_gpus': world,
-            'steps': steps, 'warmup': n_pool, 'ms_per_step': sec * 1e3 / steps, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'cfg5: epoch sweep, 402000 ten-second 4-ch chunks @ 24 kHz (4.02 M audio-s) sharded by chunk, '
-                                   'batches of %d from a resident pool of %d batches per rank (984 MB > L2)' % (B, n_pool)},
-            'epoch_seconds': sec,
-            'roofline': {'bound': 'hbm', 'achieved': algo / sec / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
-                         'frac': algo / sec / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
-                         'algorithmic_bytes_total': algo, 'note': 'per-GPU rate'},
-            'gpu_launches': int(launches), 'clocks': clocks,
-            'pool_results_reproduced_bitwise': bool(okt[0]), 'checksums_finite': finite}))
-    if world > 1:
-        dist.destroy_process_group()
+    del pool, first, last
+    if rank != 0:
+        return None
+    sec = float(t[0]) * 1e-3
+    peak, peak_src = measured_peaks()
+    algo = n_chunks * ALGO_BYTES_PER_CLIP
+    full = n_chunks == 402000
+    return {
+        'metric': 'audio-seconds/sec (cfg5 epoch sweep%s)' % ('' if full else ', scaled'), 'value': n_chunks * CLIP_S / sec, 'unit': UNIT,
+        'n_gpus': world, 'steps': steps, 'warmup': n_pool, 'ms_per_step': sec * 1e3 / steps, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'cfg5: epoch sweep, %d ten-second 4-ch chunks @ 24 kHz (%.3g M audio-s%s) sharded by chunk, '
+                               'batches of %d from a resident pool of %d batches per rank (984 MB > L2)'
+                               % (n_chunks, n_chunks * CLIP_S / 1e6, '' if full else ': %.4g of the 402000-chunk epoch' % (n_chunks / 402000.0), B, n_pool)},
+        'sweep_seconds': sec, 'epoch_seconds_extrapolated': sec * 402000.0 / n_chunks,
+        'roofline': {'bound': 'hbm', 'achieved': algo / sec / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
+                     'frac': algo / sec / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_total': algo, 'note': 'per-GPU rate'},
+        'gpu_launches': int(launches), 'clocks': clocks,
+        'pool_results_reproduced_bitwise': bool(okt[0]), 'checksums_finite': finite}
 
 
 def run_epilogue(args):
@@ -588,14 +659,51 @@ def run_ours(args):
     e2e_ms = e0.elapsed_time(e1)
     e2e_ok = bool(torch.equal(yh[:2], y[:2].cpu()))          # host path returns the same bits as the resident path
 
-    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    # ---- the roofline of e2e: the step's copies alone -- the same 245.76 MB host->device and 114.8 MB device->host,
+    # from / to the same pinned buffers, on two streams at once (PCIe is full duplex), all ranks at the same time
+    xd = torch.empty_like(x)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def copies(n):
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        s_in.wait_stream(torch.cuda.current_stream(dev)); s_out.wait_stream(torch.cuda.current_stream(dev))
+        for _ in range(n):
+            with torch.cuda.stream(s_in):
+                xd.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh.copy_(y, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(s_in); torch.cuda.current_stream(dev).wait_stream(s_out)
+        c1.record()
+        barrier()
+        return c0.elapsed_time(c1) / n
+    copies(1)
+    copy_ms = copies(e2e_steps)
+    del xd
+
+    # ---- and the same pipeline fed with 16-bit PCM (what a wav / flac decoder yields): half the host->device bytes
+    xi = (x * 32767.0).round().clamp(-32768, 32767).to(torch.int16).cpu().pin_memory()
+    for _ in range(2):
+        ext.forward_host(xi, out=yh, device=dev, chunk_clips=args.e2e_chunk, synchronize=False)
+    barrier()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(e2e_steps):
+        ext.forward_host(xi, out=yh, device=dev, chunk_clips=args.e2e_chunk, synchronize=False)
+    i1.record()
+    barrier()
+    e2e_i16_ms = i0.elapsed_time(i1)
+    del xi
+
+    t = torch.tensor([total_ms, e2e_ms, copy_ms, e2e_i16_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     # result check only (after timing): one gather of per-clip checksums, 16 B per clip, over NCCL
     from pseldnets_b200 import shard
     table = shard.gather_clip_checksums(y, world * B)
     finite = bool(torch.isfinite(table).all()) and table.shape[0] == world * B
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, copy_ms, e2e_i16_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -615,7 +723,25 @@ def run_ours(args):
         except Exception:
             pass
         cpu_threads = os.cpu_count() or 1
-        cpu_val, cpu_calls, cpu_secs = cpu_port_throughput(8, args.cpu_seconds, 200, cpu_threads)
+        cpu_val, cpu_calls, cpu_secs, cpu_kind, cpu_what = cpu_baseline_throughput(8, args.cpu_seconds, 200, cpu_threads)
+        # FP32 side of the roofline: algorithmic flops (FFT 1.0e8 + pointwise 2.3e7 + sparse mel 1.4e7 per clip)
+        # against the FP32 FMA rate measured here with a cuBLAS SGEMM (TF32 off), next to the nominal 148 SM x 128 lanes x 2
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ga = torch.randn(8192, 8192, device=dev); gb = torch.randn(8192, 8192, device=dev)
+        torch.matmul(ga, gb)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            torch.matmul(ga, gb)
+        f1.record()
+        torch.cuda.synchronize()
+        fp32_peak = 3 * 2 * 8192.0 ** 3 / (f0.elapsed_time(f1) * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        del ga, gb
+        flops_per_clip = 1.0e8 + 2.3e7 + 1.4e7
+        fp32_achieved = B * flops_per_clip / (launch_ms * 1e-3) / 1e12
         library = None
         if world == 1 and args.cpu_seconds > 0:
             # the reference's op sequence (torch.stft -> |X|^2 -> matmul -> log10, IV arithmetic: cuFFT, cuBLAS
@@ -642,23 +768,43 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'cfg2: FOA log-mel+IV, batch %d x 10 s x 4 ch @ 24 kHz per GPU -> (%d,7,1001,64)' % (B, B),
-                       'n_fft': NFFT, 'hop': HOP, 'n_mels': NMELS, 'per_gpu_batch': B, 'global_batch': B * world,
-                       'sharding': 'by clip, no collective on the data path',
-                       'l2': 'inputs 245.8 MB + outputs 114.8 MB per step exceed the 126 MB L2 (no flush needed)'},
+            'config': cfg2_config(B, world),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'seld::foa_iv2_kernel<8>',
-                         'algorithmic_bytes_per_launch': B * ALGO_BYTES_PER_CLIP, 'launch_ms': launch_ms},
-            'cpu_baseline': {'value': cpu_val, 'unit': UNIT, 'cores': cpu_threads, 'kind': 'port',
-                             'sample': '%d calls of 8 clips (10 s, 4 ch, 24 kHz) in %.1f s, torch CPU fp32 port of feature.py' % (cpu_calls, cpu_secs)},
+                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'seld::foa_iv2_kernel<8,float,true,false> (+ its redo scan <...,true>, inside the timed step)',
+                         'algorithmic_bytes_per_launch': B * ALGO_BYTES_PER_CLIP, 'launch_ms': launch_ms,
+                         'fp32_frac': fp32_achieved / fp32_peak, 'fp32_achieved_tflops': fp32_achieved,
+                         'fp32_peak_tflops': fp32_peak, 'fp32_peak_source': 'measured here: cuBLAS SGEMM 8192^3, TF32 off (nominal 148 x 128 x 2 x 1.965 GHz = 74.4)',
+                         'algorithmic_flops_per_launch': B * flops_per_clip},
+            'cpu_baseline': {'value': cpu_val, 'unit': UNIT, 'cores': cpu_threads, 'kind': cpu_kind,
+                             'sample': '%d calls of 8 clips (10 s, 4 ch, 24 kHz) in %.1f s; %s' % (cpu_calls, cpu_secs, cpu_what)},
             'e2e': {'value': audio_s * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': B * C * L * 4, 'd2h_bytes_per_step': B * (C + 3) * T * NMELS * 4,
                     'steps': e2e_steps, 'matches_resident_path': e2e_ok,
-                    'path': 'pinned host -> LogmelIV_Extractor.forward_host (seld_logmel_iv_f32_host: %d-clip chunks, H2D / kernel / D2H on 3 streams) -> pinned host' % args.e2e_chunk},
+                    'path': 'pinned host -> LogmelIV_Extractor.forward_host (seld_logmel_iv_f32_host: %d-clip chunks, H2D / kernel / D2H on 3 streams) -> pinned host' % args.e2e_chunk,
+                    # roofline of e2e: the two copies of a step on their own, concurrently, all ranks at once
+                    'copies_only_ms_per_step': copy_ms, 'ms_per_step': e2e_ms / e2e_steps, 'frac': copy_ms / (e2e_ms / e2e_steps),
+                    'copies_only_h2d_gbs': B * C * L * 4 / (copy_ms * 1e-3) / 1e9,
+                    'bound': 'host<->device copies (PCIe / host memory), measured in this run',
+                    'int16_input': {'value': audio_s * e2e_steps / (e2e_i16_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': B * C * L * 2,
+                                    'what': 'same pipeline fed with 16-bit PCM (seld_logmel_iv_i16_host), same features bit for bit'}},
             'gpu_launches': int(launches), 'clocks': clocks, 'outputs_finite': finite,
         }
         if library is not None:
             out['library_baseline_same_gpu'] = library
+    # ---- the other workloads of BASELINE.json, each with its own time, roofline fraction and clock record (N = 1; at
+    # N > 1 run them with --workload cfg3|cfg4|cfg5 under the same launcher)
+    if world == 1 and not args.no_extra:
+        del x, y, xh, yh
+        torch.cuda.empty_cache()
+        extra = {}
+        for w in ('cfg3', 'cfg4'):
+            extra[w] = extra_record(w, 30, 5, dev, rank, world)
+        extra['cfg5_scaled'] = epoch_record(4020, 64, dev, rank, world)
+        for rec in extra.values():
+            for k in ('higher_is_better', 'vs_baseline', 'dtype', 'data', 'unit', 'n_gpus', 'scaling'):
+                rec.pop(k, None)
+        out['extra'] = extra
+    if rank == 0:
         emit_json((out))
     if world > 1:
         dist.destroy_process_group()
@@ -698,6 +844,7 @@ def main():
                          '8 ch 32 kHz, global batch 128 sharded by clip (extra measurements, not the headline)')
     ap.add_argument('--cpu-seconds', type=float, default=10.0, help='bound on the cpu_baseline sample')
     ap.add_argument('--e2e-chunk', type=int, default=4, help='clips per chunk of the host-buffer pipeline (e2e)')
+    ap.add_argument('--no-extra', action='store_true', help='skip the cfg3 / cfg4 / cfg5-scaled sub-records of the default line')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -349,7 +349,10 @@ def test_bench_prints_one_json_line_with_the_contract_keys():
     assert d['n_gpus'] == 1 and d['steps'] == 20 and d['warmup'] >= 3 and d['dtype'] == 'f32' and d['vs_baseline'] is None
     r = d['roofline']
     assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] > 0
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['value'] > 0
+    assert 0 < d['e2e']['frac'] <= 1.05 and d['roofline']['fp32_frac'] > 0
+    for w in ('cfg3', 'cfg4', 'cfg5_scaled'):
+        assert d['extra'][w]['ms_per_step'] > 0 and 'sm_mhz' in d['extra'][w]['clocks'] and d['extra'][w]['roofline']['frac'] > 0
     e = d['e2e']
     assert e['h2d_bytes_per_step'] == 64 * 4 * 240000 * 4 and e['d2h_bytes_per_step'] == 64 * 7 * 1001 * 64 * 4
     assert 0 < e['value'] < d['value'] and e['matches_resident_path'] is True
