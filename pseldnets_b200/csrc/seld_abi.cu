@@ -484,7 +484,7 @@ extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B
     const bool use_top_db = top_db >= 0.0f;
     cudaError_t e = seld::mic_launch(a, p->dev, (int*)workspace, top_db, use_top_db, p->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
-    g_launches.fetch_add(use_top_db ? 2 : 1, std::memory_order_relaxed);
+    g_launches.fetch_add(use_top_db ? 3 : 2, std::memory_order_relaxed);   // features + redo scan (+ top_db floor)
     return SELD_OK;
 }
 

@@ -41,6 +41,10 @@ constexpr int kTwStride = 68;               // lane-major twiddle table row: 32 
 constexpr int kWinStride = 36;              // lane-major window table row: 32 floats + pad
 constexpr int kZeroRun = 127;               // float2 slot of every row kept at (0, 0) during the combine step
 constexpr int kRegion = kSpec + kRowsArea;
+// imbalance rule as in seld_foa_iv2.cu: a loose ratio that three of eight neighbouring bands must cross, a strict one
+// that a single band may cross; every microphone's phases enter three GCC planes, hence the loose ratio of 40 dB
+constexpr float kTauLoose = 1e-4f, kTauStrict = 1e-7f;
+constexpr uint32_t kRedoMark = 0x7fc5e1d0u;  // quiet NaN with a payload, in element 0 of the frame's first log-mel row
 
 // order-preserving float <-> int key for atomicMax
 __device__ __forceinline__ int f2key(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
@@ -66,7 +70,12 @@ __device__ __forceinline__ float2 cross_phasor(float2 ua, float2 ub) {
 //          (B, T, 513, 4) complex64, i.e. the reference's (T, F, C) layout per clip.
 // kMode 2: features from a given spectrogram in that layout (_get_logmel_spectrogram / _get_gcc, feature.py:155-175):
 //          the forward transform is skipped, everything after it is the same code.
-template <int kMode>
+// kRedo (kMode 0 only): second launch that recomputes the frames the main launch marked as too unbalanced for the packed
+//          transform -- a microphone whose mel bands lie far under those of the microphone it shares a transform with sees
+//          that one's fp32 rounding noise, and PHAT turns noise into phase.  Those frames run two passes with each
+//          microphone alone in its transform (partner slot zero): exact down to a digitally silent microphone, whose
+//          cross-spectra then vanish exactly (angle(0) = 0: phasor 1, a unit pulse at lag 0).
+template <int kMode, bool kRedo = false>
 __global__ void __launch_bounds__(mic::kW * 32, 1)
 mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey) {
     using namespace mic;
@@ -80,6 +89,17 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if constexpr (kMode == 0 && !kRedo) asm volatile("griddepcontrol.launch_dependents;");   // the redo scan may be scheduled behind us
+    if constexpr (kRedo) {                                                  // nothing marked (the normal case): leave before staging any table
+        asm volatile("griddepcontrol.wait;" ::: "memory");                  // the main grid has completed, its stores are visible
+        const int64_t n_frames = (int64_t)a.B * a.T;
+        bool mine = false;
+        for (int64_t g = ((int64_t)blockIdx.x * W + warp) * 32 + lane; g < n_frames; g += (int64_t)gridDim.x * W * 32) {
+            const int b = (int)(g / a.T), t = (int)(g - (int64_t)b * a.T);
+            mine = mine || __float_as_uint(a.out[(((int64_t)b * a.Cout) * a.T + t) * pd.n_mels]) == kRedoMark;
+        }
+        if (!__syncthreads_or(mine ? 1 : 0)) return;
+    }
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
         const float2 w = pd.tw[brev5(r) * 32 + l];                         // positions (2j, 2j+1) share one float4: (cos, cos', -sin, -sin')
@@ -127,18 +147,62 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         }
     };
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_clip;
-        const int t = (tile - b * a.tiles_per_clip) * W + warp;
-        if (t >= a.T) continue;
+    // frames of this warp: the main form walks its tiles; the redo form looks at 32 frames at a time (one per lane)
+    // and then takes the marked ones in turn
+    int tile = blockIdx.x - gridDim.x;
+    const int64_t n_frames = (int64_t)a.B * a.T;
+    const int64_t scan_step = (int64_t)gridDim.x * W * 32;
+    int64_t scan_g0 = ((int64_t)blockIdx.x * W + warp) * 32 - scan_step;
+    uint32_t todo = 0u;
+    for (;;) {
+        int b, t;
+        if constexpr (!kRedo) {
+            tile += gridDim.x;
+            if (tile >= a.n_tiles) break;
+            b = tile / a.tiles_per_clip;
+            t = (tile - b * a.tiles_per_clip) * W + warp;
+            if (t >= a.T) continue;
+        } else {
+            while (todo == 0u) {
+                scan_g0 += scan_step;
+                if (scan_g0 >= n_frames) break;
+                const int64_t g = scan_g0 + lane;
+                bool marked = false;
+                if (g < n_frames) {
+                    const int gb = (int)(g / a.T), gt = (int)(g - (int64_t)gb * a.T);
+                    marked = __float_as_uint(a.out[(((int64_t)gb * a.Cout) * a.T + gt) * M]) == kRedoMark;
+                }
+                todo = __ballot_sync(0xffffffffu, marked);
+            }
+            if (todo == 0u) break;
+            const int64_t gg = scan_g0 + (__ffs(todo) - 1);
+            todo &= todo - 1;
+            b = (int)(gg / a.T);
+            t = (int)(gg - (int64_t)b * a.T);
+        }
         if (b != cur_b) { flush_max(); cur_b = b; }
         const float* xb = static_cast<const float*>(a.x) + (int64_t)b * a.stride_b;
         const int64_t s0 = (int64_t)t * hop - 512;
 
         float2 re[32], im[32];
         float* const spec_g = static_cast<float*>(a.spec) + (((int64_t)b * a.T + t) * 513) * 8;   // kMode 1 / 2: this frame's (513, 4) complex block
+        float2 keep02[17];                                                  // kRedo: (|X0|^2, |X2|^2) of pass 0, written as rows after pass 1's exchange
+        float min_n = 1.0f;                                                 // becomes 0 if any channel has a vanishing bin
+#pragma unroll 1
+        for (int pass = 0; pass < (kRedo ? 2 : 1); ++pass) {
         if constexpr (kMode != 2) {
         // ---------------- load + window: re = (mic0, mic2), im = (mic1, mic3); zeros outside the clip
+        if constexpr (kRedo) {                                              // pass p: re = (mic p, mic p+2), im = 0
+            const float* pa = xb + (int64_t)pass * a.stride_c;
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                const int64_t s = s0 + 32 * m + lane;
+                const bool in = s >= 0 && s < a.L;
+                const float* p = pa + (in ? s : 0);
+                re[m] = in ? make_float2(__ldg(p), __ldg(p + 2 * a.stride_c)) : make_float2(0.f, 0.f);
+                im[m] = make_float2(0.f, 0.f);
+            });
+        } else
         if (s0 >= 0 && s0 + 1024 <= a.L) {
             const float* p0 = xb + s0 + lane;
             const float* p1 = p0 + a.stride_c;
@@ -204,7 +268,6 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         }  // kMode != 2
 
         // ---------------- untangle: spectra -> spec[c][k], powers -> rows
-        float min_n = 1.0f;                                                 // becomes 0 if any channel has a vanishing bin
         static_for<0, 17>([&](auto kbi) {
             constexpr int kb = decltype(kbi)::value;
             constexpr int p = brev5(kb & 31);
@@ -243,6 +306,26 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             }
             const float2 p02 = __ffma2_rn(ai, ai, __fmul2_rn(ar, ar));
             const float2 p13 = __ffma2_rn(bi, bi, __fmul2_rn(br, br));
+            if constexpr (kRedo) {
+                // the live slots are (mic pass, mic pass + 2) = (ar, ai); the other two are zero
+                if (kb < 16 || lane == 0) {
+                    const int k = lane + 32 * kb;
+                    const float2 n02 = make_float2(inv_mag(p02.x), inv_mag(p02.y));
+                    min_n = fminf(min_n, fminf(n02.x, n02.y));
+                    const float2 ur = __fmul2_rn(ar, n02), ui = __fmul2_rn(ai, n02);
+                    spec[pass * kSpecStride + k] = make_float2(ur.x, ui.x);
+                    spec[(pass + 2) * kSpecStride + k] = make_float2(ur.y, ui.y);
+                    if (pass == 1) {
+                        float* q = R + 32 * kb + wofs[kb & 3];
+                        q[0 * kRowWords] = keep02[kb].x;
+                        q[1 * kRowWords] = p02.x;
+                        q[2 * kRowWords] = keep02[kb].y;
+                        q[3 * kRowWords] = p02.y;
+                    }
+                }
+                if (pass == 0) keep02[kb] = p02;
+                return;
+            }
             if (kb < 16 || lane == 0) {
                 const int k = lane + 32 * kb;
                 // PHAT only needs phases: keep X_c / |X_c| (unit phasors) for the GCC passes
@@ -262,6 +345,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             }
         });
         __syncwarp();
+        }  // pass
         if constexpr (kMode == 1) continue;
 
         // ---------------- log-mel of the four power rows (unclamped dB + running maximum)
@@ -274,7 +358,19 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             __syncwarp();
             // band per lane; run numbers of segment m (V) and m+1 (U) in fixed slots (absent -> the zero run), all
             // loads issued up front (n_mels == 64 on this path: bands lane and lane + 32)
-            uint32_t quiet = 15u;                                           // bit c: mic c looks silent in both of this lane's bands
+            bool bad = false;                                               // some microphone too far under its transform partner
+            float rmax0[4];                                                 // the maxima before this frame (a marked frame must not count)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) rmax0[f] = rmax[f];
+            auto unbalanced = [](const float (&v)[4], float t) {
+                return v[0] < t * v[1] || v[1] < t * v[0] || v[2] < t * v[3] || v[3] < t * v[2];
+            };
+            auto clustered = [](uint32_t m) {                               // an aligned group of eight bands with >= 3 bits set
+                uint32_t c = m - ((m >> 1) & 0x55555555u);
+                c = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);
+                c = (c + (c >> 4)) & 0x0f0f0f0fu;
+                return ((c + 0x05050505u) & 0x08080808u) != 0u;
+            };
             auto combine = [&](auto four_c) {
                 constexpr bool kFour = decltype(four_c)::value;
 #pragma unroll
@@ -296,11 +392,10 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                             v[f] = ((v0 + v1) + v2) + ((u0 + u1) + u2);
                         }
                     }
-                    // silent-microphone screen (see below): band power more than 120 dB under the transform partner's
-                    constexpr float kRel = 1e-12f;
-                    const bool d0 = v[0] < kRel * v[1], d1 = v[1] < kRel * v[0], d2 = v[2] < kRel * v[3], d3 = v[3] < kRel * v[2];
-                    quiet &= (d0 ? 1u : 0u) | (d1 ? 2u : 0u) | (d2 ? 4u : 0u) | (d3 ? 8u : 0u);
-                    v[0] = d0 ? 0.0f : v[0]; v[1] = d1 ? 0.0f : v[1]; v[2] = d2 ? 0.0f : v[2]; v[3] = d3 ? 0.0f : v[3];
+                    if constexpr (kMode == 0 && !kRedo) {                   // every lane votes (no short-circuit in front of the ballot)
+                        const uint32_t lm = __ballot_sync(0xffffffffu, unbalanced(v, kTauLoose));
+                        bad = clustered(lm) || unbalanced(v, kTauStrict) || bad;
+                    }
 #pragma unroll
                     for (int f = 0; f < 4; ++f) {
                         const float db = 3.01029995663981195f * lg2_ftz(fmaxf(v[f], amin));
@@ -311,18 +406,14 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             };
             if (four) combine(std::true_type{}); else combine(std::false_type{});
             __syncwarp();                                                   // rows become the exchange buffer again
-            // A microphone whose frame is digitally silent must have an exactly zero spectrum (its cross-spectra then
-            // have angle(0) = 0, phasor 1), but it shares a packed transform with another one (0 with 1, 2 with 3) and
-            // came out of the untangle step as that one's rounding noise, <= -130 dB relative, which PHAT would turn
-            // into random phases.  A microphone more than 120 dB under its partner in every mel band -- below what the
-            // packed fp32 transform resolves -- is taken to be silent: its phasors are cleared (rare path).
-            const uint32_t dead = __reduce_and_sync(0xffffffffu, quiet);
-            if (dead != 0) {
-                for (int c = 0; c < 4; ++c)
-                    if (dead >> c & 1)
-                        for (int k = lane; k <= 512; k += 32) spec[c * kSpecStride + k] = make_float2(0.f, 0.f);
-                min_n = 0.0f;
-                __syncwarp();
+            if constexpr (kMode == 0 && !kRedo) {
+                if (__any_sync(0xffffffffu, bad)) {
+                    // leave the frame to the redo launch: mark it, take its values back out of the running maxima
+                    if (lane == 0) ob[0] = __uint_as_float(kRedoMark);      // lane 0 wrote that element itself: program order
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) rmax[f] = rmax0[f];
+                    continue;
+                }
             }
         }
 
@@ -514,6 +605,20 @@ static cudaError_t mic_set_attr() {
     return cudaSuccess;
 }
 
+static cudaError_t mic_set_attr_redo() {
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_relaxed) & bit)) {
+        e = cudaFuncSetAttribute(mic_features_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        done.fetch_or(bit, std::memory_order_relaxed);
+    }
+    return cudaSuccess;
+}
+
 // waveform -> (B, T, 513, 4) complex64 spectrogram in a.spec
 cudaError_t mic_spectrogram_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
     cudaError_t e = mic_set_attr<1>();
@@ -532,9 +637,26 @@ cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float t
     e = cudaMemsetAsync(maxkey, 0x80, (size_t)a.B * 4 * sizeof(int), st);  // key 0x80808080: below any dB value
     if (e != cudaSuccess) return e;
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
-    if (from_spectra) mic_features_kernel<2><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
-    else mic_features_kernel<0><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
-    e = cudaGetLastError();
+    if (from_spectra) {
+        mic_features_kernel<2><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
+        e = cudaGetLastError();
+    } else {
+        mic_features_kernel<0><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // frames the main launch marked as too unbalanced for the packed transform (normally none), before the floor
+        e = mic_set_attr_redo();
+        if (e != cudaSuccess) return e;
+        const int64_t blocks = ((int64_t)a.B * a.T + 32 * mic::kW - 1) / (32 * mic::kW);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(blocks < sm_count ? blocks : sm_count)); cfg.blockDim = dim3(mic::kW * 32);
+        cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, mic_features_kernel<0, true>, a, pd, maxkey);
+    }
     if (e != cudaSuccess || !use_top_db) return e;
     const int64_t plane = (int64_t)a.T * pd.n_mels;                         // multiple of 4 (n_mels = 64)
     dim3 grid((unsigned)((plane / 4 + 255) / 256 > 64 ? 64 : (plane / 4 + 255) / 256), (unsigned)(a.B * 4));

@@ -227,3 +227,18 @@ def test_mic_reference_stage_methods_run_preprocess_unchanged():
     assert sp.shape == (9, 513, 4)
     lm = front._get_logmel_spectrogram(sp.copy())
     assert lm.shape == (9, 64, 4) and np.isfinite(lm).all()
+
+
+@pytest.mark.parametrize('quiet', [0, 1, 2, 3])
+@pytest.mark.parametrize('db', [20, 40, 60, 80, 100])
+def test_mic_microphone_attenuated_against_its_partner(quiet, db):
+    """Finite level imbalance inside a microphone pair that shares a packed transform (0/1 and 2/3): PHAT keeps only
+    phases, so the partner's rounding noise in a quiet microphone's spectrum shows in every GCC plane of that
+    microphone.  Frames whose microphones are too far apart are transformed again with each microphone alone
+    (as the FOA kernels do)."""
+    from oracle import synth
+    ext = _mic()
+    x = synth.uniform(700 + 10 * quiet + db, (2, 4, 4800)).astype(np.float32)
+    x[:, quiet] *= np.float32(10.0 ** (-db / 20.0))
+    y = ext(torch.from_numpy(x).cuda()).cpu().numpy()
+    _check(y, _oracle(ext, x), 'microphone %d at -%d dB' % (quiet, db))
