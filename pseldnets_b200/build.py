@@ -16,8 +16,11 @@ SOURCES = ['seld_foa.cu', 'seld_foa_iv2.cu', 'seld_mic.cu', 'seld_epilogue.cu', 
 # projection iv5, two-warps-per-frame iv3, 12-warp iv2), selectable with SELD_IV_KERNEL=5 / 3 / SELD_IV2_WARPS=12;
 # the product library ships without them.
 EXPERIMENT_SOURCES = ['seld_foa_iv5.cu', 'seld_foa_iv3.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
+# -rdc=true + cudadevrt: the FOA / MIC kernels launch their own redo form from the device (cudaStreamTailLaunch) for the rare
+# frames whose channels are too unbalanced for the packed transform -- ordinary input then costs no second launch
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-rdc=true',
               '-Xcompiler', '-fPIC', '-shared']
+NVCC_LIBS = ['-lcudadevrt']
 
 
 def _newest_source_mtime():
@@ -36,7 +39,7 @@ def build(force=False, verbose=False):
     experiments = os.environ.get('SELD_EXPERIMENTS', '') not in ('', '0')
     sources = SOURCES + (EXPERIMENT_SOURCES if experiments else [])
     cmd = [nvcc] + NVCC_FLAGS + (['-DSELD_EXPERIMENTS'] if experiments else []) + (['-Xptxas', '-v'] if verbose else []) + \
-          ['-o', LIB] + [os.path.join(CSRC, s) for s in sources]
+          ['-o', LIB] + [os.path.join(CSRC, s) for s in sources] + NVCC_LIBS
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)

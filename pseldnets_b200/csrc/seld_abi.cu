@@ -329,7 +329,7 @@ static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C,
 #endif
         else e = seld::foa_iv2_launch(a, p->dev, p->sm_count, st);
         if (e != cudaSuccess) return cuda_fail(e);
-        g_launches.fetch_add(kern == 2 ? 2 : 1, std::memory_order_relaxed);   // iv2: main kernel + its redo scan
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         if (C == 4) return SELD_OK;
         a.c_lo = 4; general_iv = false;
     }
@@ -342,7 +342,7 @@ static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C,
         a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc);
         cudaError_t e = seld::foa_lm4_launch(a, p->dev, p->sm_count, st);
         if (e != cudaSuccess) return cuda_fail(e);
-        g_launches.fetch_add(2, std::memory_order_relaxed);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         return SELD_OK;
     }
     const int fpt = seld::foa_frames_per_tile();
@@ -484,7 +484,7 @@ extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B
     const bool use_top_db = top_db >= 0.0f;
     cudaError_t e = seld::mic_launch(a, p->dev, (int*)workspace, top_db, use_top_db, p->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
-    g_launches.fetch_add(use_top_db ? 3 : 2, std::memory_order_relaxed);   // features + redo scan (+ top_db floor)
+    g_launches.fetch_add(use_top_db ? 2 : 1, std::memory_order_relaxed);
     return SELD_OK;
 }
 

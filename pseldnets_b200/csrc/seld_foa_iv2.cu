@@ -54,10 +54,13 @@ constexpr int kWabStride = 36;            // floats per lane in the (a, b) weigh
 // per-block list and transformed again at the end of the kernel with every channel alone in its transform (the
 // partner slot zero), which is exact down to digital silence.  Ordinary material never takes that path.
 // Mechanics: the main kernel marks such a frame by a sentinel (a NaN pattern no arithmetic produces) in element 0 of
-// one of its output rows; a second launch of the same kernel template in its kRedo form scans for sentinels and
-// recomputes those frames.  (A tail inside the main kernel was measured: it wrecks the register allocation of the
-// main loop, 0.73 ms instead of 0.41 ms.)  No state outside the output tensor, so calls on different streams do not
-// interact.
+// one of its output rows.  A block that marked anything launches, from the device and into the tail of its own grid
+// (cudaStreamTailLaunch: it runs once the whole main grid has finished, and the stream's next kernel waits for it),
+// one block of the same kernel template in its kRedo form, which looks through that block's frames for sentinels and
+// recomputes them.  Ordinary material launches nothing.  (Measured alternatives: the slow path inside the main kernel
+// wrecks the register allocation of the main loop, 0.73 ms instead of 0.41 ms; an unconditional second launch from
+// the host that scans all frames costs 10 us per call.)  No state outside the output tensor, so calls on different
+// streams do not interact.
 // Band powers of stationary noise fluctuate (a narrow band is a chi-square with few degrees of freedom), so a single
 // band far under its partner's is no evidence of a level difference between channels: the loose thresholds only
 // count when three of eight neighbouring bands agree; one band alone must cross the strict threshold.
@@ -87,18 +90,25 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride
     int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
     float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
+    int* marked_s = reinterpret_cast<int*>(R_all + W * kRegion);           // main form: some warp of this block marked a frame
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float in_scale = a.in_scale;
-    // redo form: groups of work (kIV: frames; log-mel only: groups of four (frame, channel) jobs, as in the main form)
-    // and the test for the main kernel's mark in element 0 of a group's output rows
+    // redo form: the work items of main block `a.redo_block`: its tiles redo_block, + redo_grid, ..., W items each
+    // (kIV: frames; log-mel only: groups of four (frame, channel) jobs), item j = (tile number j / W, warp slot j % W)
     const int redo_Cj = a.C - a.c_lo;
     const int64_t redo_J = (int64_t)a.T * redo_Cj;                          // log-mel only: jobs per clip
-    const int64_t redo_gpc = kIV ? (int64_t)a.T : (redo_J + 3) / 4;         // groups per clip
-    const int64_t redo_groups = (int64_t)a.B * redo_gpc;
-    auto is_marked = [&](int64_t g) -> bool {
-        if (g >= redo_groups) return false;
-        const int b = (int)(g / redo_gpc), grp = (int)(g - (int64_t)b * redo_gpc);
+    const int redo_tiles = (kRedo && a.n_tiles > a.redo_block) ? (a.n_tiles - 1 - a.redo_block) / a.redo_grid + 1 : 0;
+    const int redo_items = redo_tiles * W;
+    auto redo_item = [&](int j, int& b, int& grp) -> bool {                 // false: no such frame / group
+        const int tile = a.redo_block + (j / W) * a.redo_grid;
+        b = tile / a.tiles_per_clip;
+        grp = (tile - b * a.tiles_per_clip) * W + (j % W);
+        return kIV ? grp < a.T : (int64_t)4 * grp < redo_J;
+    };
+    auto is_marked = [&](int j) -> bool {
+        int b, grp;
+        if (j >= redo_items || !redo_item(j, b, grp)) return false;
         const float* const o0 = a.out + ((int64_t)b * a.Cout) * ((int64_t)a.T * pd.n_mels);
         if constexpr (kIV) {
             return __float_as_uint(o0[((int64_t)a.C * a.T + grp) * pd.n_mels]) == kRedoMark;
@@ -106,25 +116,13 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             bool marked = false;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int64_t j = (int64_t)4 * grp + q;
-                if (j < redo_J)
-                    marked = marked || __float_as_uint(o0[((int64_t)(a.c_lo + (int)(j % redo_Cj)) * a.T + (j / redo_Cj)) * pd.n_mels]) == kRedoMark;
+                const int64_t jj = (int64_t)4 * grp + q;
+                if (jj < redo_J)
+                    marked = marked || __float_as_uint(o0[((int64_t)(a.c_lo + (int)(jj % redo_Cj)) * a.T + (jj / redo_Cj)) * pd.n_mels]) == kRedoMark;
             }
             return marked;
         }
     };
-    if constexpr (!kRedo) {
-        // the redo scan is launched with programmatic stream serialisation: let it be scheduled while this grid runs
-        // (its blocks only become resident as ours retire, and wait for the whole grid before they read anything)
-        asm volatile("griddepcontrol.launch_dependents;");
-    }
-    if constexpr (kRedo) {                                                  // nothing marked (the normal case): leave before staging any table
-        asm volatile("griddepcontrol.wait;" ::: "memory");                  // the main grid has completed and its stores are visible
-        bool mine = false;
-        for (int64_t g0 = ((int64_t)blockIdx.x * W + warp) * 32; g0 < redo_groups; g0 += (int64_t)gridDim.x * W * 32)
-            mine = mine || is_marked(g0 + lane);
-        if (!__syncthreads_or(mine ? 1 : 0)) return;
-    }
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
         const float2 w = pd.tw[brev5(r) * 32 + l];
@@ -133,6 +131,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     }
     for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
     for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
+    if (tid == 0) *marked_s = 0;
     __syncthreads();
 
     float* R = R_all + warp * kRegion;
@@ -514,6 +513,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 
         const bool bad = mel_rows(std::true_type{}, b, t, tk, ck, vk);
         if (__any_sync(0xffffffffu, bad) && lane == 0) {                    // lane 0 also wrote element 0 of every row: program order
+            *marked_s = 1;
             float* const o0 = a.out + ((int64_t)b * a.Cout) * ch_stride;
             if constexpr (kIV) {
                 o0[(int64_t)a.C * ch_stride + (int64_t)t * M] = __uint_as_float(kRedoMark);
@@ -526,6 +526,12 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         __syncwarp();                                                       // rows are reused by the next frame's exchange
         PHASE_MARK(8);   // mel combine + store
     }
+    __syncthreads();
+    if (tid == 0 && *marked_s != 0) {
+        FoaArgs ar = a;
+        ar.redo_block = (int)blockIdx.x; ar.redo_grid = (int)gridDim.x;
+        foa_iv2_kernel<W, TIn, kIV, true><<<1, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd);
+    }
 
     } else {
     // ---------------- frames whose channels were too unbalanced for the packed transform: once more, every slot alone
@@ -533,7 +539,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     // silent channel comes out as exact zeros, like the reference's one-FFT-per-channel, feature.py:49)
     {
         const int Cj = redo_Cj;
-        const int64_t J = redo_J, gpc = redo_gpc;
+        const int64_t J = redo_J;
         auto redo = [&](int b, int grp) {
             int tk[4] = {grp, grp, grp, grp}, ck[4] = {0, 1, 2, 3};
             bool vk[4] = {true, true, true, true};
@@ -649,17 +655,15 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             mel_rows(std::false_type{}, b, tk[0], tk, ck, vk);
             __syncwarp();
         };
-        // scan: a warp looks at 32 groups at a time (one per lane), then redoes the marked ones
-        const int64_t wid = (int64_t)blockIdx.x * W + warp, nw = (int64_t)gridDim.x * W;
-        for (int64_t g0 = wid * 32; g0 < redo_groups; g0 += nw * 32) {
-            const bool marked = is_marked(g0 + lane);
-            uint32_t todo = __ballot_sync(0xffffffffu, marked);
+        // scan: a warp looks at 32 items at a time (one per lane), then redoes the marked ones
+        for (int j0 = warp * 32; j0 < redo_items; j0 += W * 32) {
+            uint32_t todo = __ballot_sync(0xffffffffu, is_marked(j0 + lane));
             while (todo) {
                 const int l = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int64_t gg = g0 + l;
-                const int b = (int)(gg / gpc);
-                redo(b, (int)(gg - (int64_t)b * gpc));
+                int b, grp;
+                redo_item(j0 + l, b, grp);
+                redo(b, grp);
             }
         }
     }
@@ -672,7 +676,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 // ---------------------------------------------------------------------------------------------
 template <int W>
 static size_t iv2_smem_bytes(const PlanDev& pd) {
-    return (size_t)(32 * kTwStride + 32 * kWinStride + 32 * kWabStride + pd.gseg_pad + W * kRegion) * sizeof(float);
+    return (size_t)(32 * kTwStride + 32 * kWinStride + 32 * kWabStride + pd.gseg_pad + W * kRegion + 4) * sizeof(float);
 }
 
 // Warps (= frames) per block.  One block per SM; more warps hide latency, fewer leave more
@@ -715,21 +719,9 @@ static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_coun
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
     FoaArgs aa = a;
     aa.step_clip = gx / a.tiles_per_clip; aa.step_tile = gx - aa.step_clip * a.tiles_per_clip;
+    aa.smem_bytes = (int)smem;                                              // blocks that mark frames launch the redo form themselves
     foa_iv2_kernel<W, TIn, kIV><<<gx, W * 32, smem, st>>>(aa, pd);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    // second launch: frames the main kernel marked as too unbalanced for the packed transform (normally none: the
-    // kernel then only scans one output element per frame)
-    const int64_t groups = (int64_t)a.B * (kIV ? (int64_t)a.T : ((int64_t)a.T * (a.C - a.c_lo) + 3) / 4);
-    const int64_t blocks = (groups + 32 * W - 1) / (32 * W);
-    const int gr = (int)(blocks < sm_count ? blocks : sm_count);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)gr); cfg.blockDim = dim3(W * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, foa_iv2_kernel<W, TIn, kIV, true>, aa, pd);
+    return cudaGetLastError();
 }
 
 #ifdef SELD_PHASE_TIMING

@@ -87,19 +87,9 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride
     int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
     float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
+    int* marked_s = reinterpret_cast<int*>(R_all + W * kRegion);           // main form: some warp of this block marked a frame
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if constexpr (kMode == 0 && !kRedo) asm volatile("griddepcontrol.launch_dependents;");   // the redo scan may be scheduled behind us
-    if constexpr (kRedo) {                                                  // nothing marked (the normal case): leave before staging any table
-        asm volatile("griddepcontrol.wait;" ::: "memory");                  // the main grid has completed, its stores are visible
-        const int64_t n_frames = (int64_t)a.B * a.T;
-        bool mine = false;
-        for (int64_t g = ((int64_t)blockIdx.x * W + warp) * 32 + lane; g < n_frames; g += (int64_t)gridDim.x * W * 32) {
-            const int b = (int)(g / a.T), t = (int)(g - (int64_t)b * a.T);
-            mine = mine || __float_as_uint(a.out[(((int64_t)b * a.Cout) * a.T + t) * pd.n_mels]) == kRedoMark;
-        }
-        if (!__syncthreads_or(mine ? 1 : 0)) return;
-    }
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
         const float2 w = pd.tw[brev5(r) * 32 + l];                         // positions (2j, 2j+1) share one float4: (cos, cos', -sin, -sin')
@@ -108,6 +98,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     }
     for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
     for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
+    if (tid == 0) *marked_s = 0;
     __syncthreads();
 
     float2* spec = reinterpret_cast<float2*>(R_all + warp * kRegion);      // [4][kSpecStride]
@@ -150,9 +141,17 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     // frames of this warp: the main form walks its tiles; the redo form looks at 32 frames at a time (one per lane)
     // and then takes the marked ones in turn
     int tile = blockIdx.x - gridDim.x;
-    const int64_t n_frames = (int64_t)a.B * a.T;
-    const int64_t scan_step = (int64_t)gridDim.x * W * 32;
-    int64_t scan_g0 = ((int64_t)blockIdx.x * W + warp) * 32 - scan_step;
+    // redo form (one block, launched from the device by block a.redo_block of a main grid of a.redo_grid blocks): item j
+    // = (tile number j / W of that block, warp slot j % W)
+    const int redo_tiles = (kRedo && a.n_tiles > a.redo_block) ? (a.n_tiles - 1 - a.redo_block) / a.redo_grid + 1 : 0;
+    const int redo_items = redo_tiles * W;
+    auto redo_item = [&](int j, int& b, int& t) -> bool {
+        const int tl = a.redo_block + (j / W) * a.redo_grid;
+        b = tl / a.tiles_per_clip;
+        t = (tl - b * a.tiles_per_clip) * W + (j % W);
+        return j < redo_items && t < a.T;
+    };
+    int scan_j0 = warp * 32 - W * 32;
     uint32_t todo = 0u;
     for (;;) {
         int b, t;
@@ -164,21 +163,17 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             if (t >= a.T) continue;
         } else {
             while (todo == 0u) {
-                scan_g0 += scan_step;
-                if (scan_g0 >= n_frames) break;
-                const int64_t g = scan_g0 + lane;
+                scan_j0 += W * 32;
+                if (scan_j0 >= redo_items) break;
+                int gb, gt;
                 bool marked = false;
-                if (g < n_frames) {
-                    const int gb = (int)(g / a.T), gt = (int)(g - (int64_t)gb * a.T);
+                if (redo_item(scan_j0 + lane, gb, gt))
                     marked = __float_as_uint(a.out[(((int64_t)gb * a.Cout) * a.T + gt) * M]) == kRedoMark;
-                }
                 todo = __ballot_sync(0xffffffffu, marked);
             }
             if (todo == 0u) break;
-            const int64_t gg = scan_g0 + (__ffs(todo) - 1);
+            redo_item(scan_j0 + (__ffs(todo) - 1), b, t);
             todo &= todo - 1;
-            b = (int)(gg / a.T);
-            t = (int)(gg - (int64_t)b * a.T);
         }
         if (b != cur_b) { flush_max(); cur_b = b; }
         const float* xb = static_cast<const float*>(a.x) + (int64_t)b * a.stride_b;
@@ -409,7 +404,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             if constexpr (kMode == 0 && !kRedo) {
                 if (__any_sync(0xffffffffu, bad)) {
                     // leave the frame to the redo launch: mark it, take its values back out of the running maxima
-                    if (lane == 0) ob[0] = __uint_as_float(kRedoMark);      // lane 0 wrote that element itself: program order
+                    if (lane == 0) { ob[0] = __uint_as_float(kRedoMark); *marked_s = 1; }   // lane 0 wrote that element itself: program order
 #pragma unroll
                     for (int f = 0; f < 4; ++f) rmax[f] = rmax0[f];
                     continue;
@@ -560,6 +555,16 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         }
     }
     flush_max();
+    if constexpr (kMode == 0 && !kRedo) {
+        // a block that marked frames launches the redo form for them into the tail of this grid: it runs when the whole
+        // grid is done and before the stream's next kernel (the top_db floor)
+        __syncthreads();
+        if (tid == 0 && *marked_s != 0) {
+            FoaArgs ar = a;
+            ar.redo_block = (int)blockIdx.x; ar.redo_grid = (int)gridDim.x;
+            mic_features_kernel<0, true><<<1, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd, maxkey);
+        }
+    }
 }
 
 // top_db floor of the log-mel planes: v = max(v, max_over_plane - top_db)
@@ -581,7 +586,7 @@ __global__ void mic_topdb_kernel(float* __restrict__ out, const int* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 static size_t mic_smem_bytes(const PlanDev& pd) {
-    return (size_t)(32 * mic::kTwStride + 32 * mic::kWinStride + 32 * melseg::kWabStride + pd.gseg_pad + mic::kW * mic::kRegion) * sizeof(float);
+    return (size_t)(32 * mic::kTwStride + 32 * mic::kWinStride + 32 * melseg::kWabStride + pd.gseg_pad + mic::kW * mic::kRegion + 4) * sizeof(float);
 }
 
 bool mic_supported(const PlanDev& pd, size_t smem_optin) {
@@ -641,21 +646,12 @@ cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float t
         mic_features_kernel<2><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
         e = cudaGetLastError();
     } else {
-        mic_features_kernel<0><<<gx, mic::kW * 32, smem, st>>>(a, pd, maxkey);
+        e = mic_set_attr_redo();                                          // the device-side launch of the redo form needs its opt-in too
+        if (e != cudaSuccess) return e;
+        FoaArgs aa = a;
+        aa.smem_bytes = (int)smem;
+        mic_features_kernel<0><<<gx, mic::kW * 32, smem, st>>>(aa, pd, maxkey);
         e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        // frames the main launch marked as too unbalanced for the packed transform (normally none), before the floor
-        e = mic_set_attr_redo();
-        if (e != cudaSuccess) return e;
-        const int64_t blocks = ((int64_t)a.B * a.T + 32 * mic::kW - 1) / (32 * mic::kW);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(blocks < sm_count ? blocks : sm_count)); cfg.blockDim = dim3(mic::kW * 32);
-        cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, mic_features_kernel<0, true>, a, pd, maxkey);
     }
     if (e != cudaSuccess || !use_top_db) return e;
     const int64_t plane = (int64_t)a.T * pd.n_mels;                         // multiple of 4 (n_mels = 64)
