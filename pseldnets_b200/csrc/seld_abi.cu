@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <new>
 #include <vector>
@@ -75,6 +76,11 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     std::vector<uint32_t> runmask(32, 0);
     std::vector<int> g0(32, 0), gseg(n_mels + 2, 0);
     int fast_ok = (F == 513);
+    // item form (see PlanDev): pieces of segments, one piece per lane and class
+    std::vector<float> iw;
+    std::vector<int> istart(4 * 32, 0);
+    std::vector<uint32_t> islot((size_t)n_mels * 2, 0);
+    int item_ok = 0, iP = 0, iK = 0, iL[4] = {0, 0, 0, 0}, ioff[4] = {0, 0, 0, 0};
     {
         std::vector<int> seg(F, 0);
         int sprev = 0;
@@ -84,7 +90,11 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                 if (fb_host[(size_t)k * n_mels + m] != 0.0f) { if (first < 0) first = m; last = m; ++cnt; }
             int sk;
             if (cnt == 0) sk = sprev;
-            else if (cnt == 1) sk = (sprev == first || sprev == first + 1) ? sprev : first;
+            else if (cnt == 1) {
+                sk = (sprev == first || sprev == first + 1) ? sprev : first;
+                // past the peak of a band with no upper neighbour here (the last band): its falling slope is the next segment
+                if (sk == first && k > 0 && fb_host[(size_t)k * n_mels + first] < fb_host[(size_t)(k - 1) * n_mels + first]) sk = first + 1;
+            }
             else if (cnt == 2 && last == first + 1) sk = last;
             else { fast_ok = 0; break; }
             if (sk < sprev) { fast_ok = 0; break; }
@@ -112,7 +122,93 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
             for (int sgm = 0; sgm <= n_mels; ++sgm)
                 if (gseg[sgm + 1] - gseg[sgm] > 4) fast_ok = 0;   // the combine step reads <= 4 runs per segment
         }
+        if (fast_ok && n_mels <= 64) {
+            // ---- item form.  Bins of segment s (those with a non-zero weight), cut into near-equal pieces of at most
+            // `maxlen` bins; the 32 longest pieces form class 0, the next 32 class 1, ...; a class is as long as its longest
+            // piece.  Choose (classes, maxlen) for the least work per frame: positions (each costs the per-bin arithmetic
+            // and four loads) plus a per-class cost (its sums are stored and read back once).
+            struct Piece { int lo, n, seg; };
+            std::vector<int> slo(n_mels + 1, F), shi(n_mels + 1, -1);
+            for (int k = 0; k < F; ++k) {
+                const int sk = seg[k];
+                const float wa = sk >= 1 ? fb_host[(size_t)k * n_mels + sk - 1] : 0.0f, wb = sk < n_mels ? fb_host[(size_t)k * n_mels + sk] : 0.0f;
+                if (wa != 0.0f || wb != 0.0f) { if (k < slo[sk]) slo[sk] = k; shi[sk] = k; }
+            }
+            std::vector<Piece> best; int bestK = 0; long bestCost = -1;
+            for (int K = 1; K <= 4; ++K)
+                for (int maxlen = 1; maxlen <= 24; ++maxlen) {
+                    std::vector<Piece> pc; bool ok = true;
+                    for (int sgm = 0; sgm <= n_mels && ok; ++sgm) {
+                        if (shi[sgm] < 0) continue;
+                        const int n = shi[sgm] - slo[sgm] + 1, np = (n + maxlen - 1) / maxlen;
+                        if (np > 4) { ok = false; break; }            // the combine step reads <= 4 pieces per segment
+                        int at = slo[sgm];
+                        for (int i = 0; i < np; ++i) { const int len = n / np + (i < n % np ? 1 : 0); pc.push_back({at, len, sgm}); at += len; }
+                    }
+                    if (!ok || (int)pc.size() > 32 * K || pc.empty()) continue;
+                    std::stable_sort(pc.begin(), pc.end(), [](const Piece& x, const Piece& y) { return x.n > y.n; });
+                    int P = 0;
+                    for (int c = 0; c < K; ++c) if ((size_t)(32 * c) < pc.size()) P += pc[32 * c].n;
+                    const long cost = 14L * P + 20L * K;
+                    if (bestCost < 0 || cost < bestCost) { bestCost = cost; best = pc; bestK = K; }
+                }
+            if (bestCost >= 0) {
+                iK = bestK;
+                for (int c = 0; c < 4; ++c) { iL[c] = (c < iK && (size_t)(32 * c) < best.size()) ? best[32 * c].n : 0; }
+                for (int c = 0; c < 4; ++c) { ioff[c] = iP; iP += iL[c]; }
+                if (iP >= 8 && iP <= 24) {
+                    item_ok = 1;
+                    // Placement: lane l reads positions ioff[c] .. ioff[c] + iL[c] of class c from bins istart[c][l] + j of the
+                    // rows (natural bin order), with weight zero outside its piece.  A warp-wide 64-bit load is conflict-free
+                    // when the 16 lanes of each half-warp start at 16 different residues mod 16; a piece shorter than its
+                    // class may start up to iL[c] - n bins early, which is what makes the residues assignable.
+                    iw.assign((size_t)iP * 32 * 2, 0.0f);
+                    std::vector<std::vector<int>> seg_slots(n_mels + 2);
+                    for (int c = 0; c < iK; ++c) {
+                        std::vector<Piece> cl(best.begin() + std::min(best.size(), (size_t)32 * c), best.begin() + std::min(best.size(), (size_t)32 * (c + 1)));
+                        int lane_piece[32], lane_start[32];
+                        bool used[2][16] = {};
+                        for (int l = 0; l < 32; ++l) { lane_piece[l] = -1; lane_start[l] = -1; }
+                        std::vector<int> left;
+                        for (size_t i = 0; i < cl.size(); ++i) {             // longest (least freedom) first: cl is sorted by length
+                            bool placed = false;
+                            for (int d = 0; d <= iL[c] - cl[i].n && d <= cl[i].lo && !placed; ++d) {
+                                const int st = cl[i].lo - d, r = st & 15;
+                                for (int h = 0; h < 2 && !placed; ++h) {
+                                    if (used[h][r]) continue;
+                                    const int l = 16 * h + r;              // lane = residue inside its half-warp
+                                    used[h][r] = true; lane_piece[l] = (int)i; lane_start[l] = st; placed = true;
+                                }
+                            }
+                            if (!placed) left.push_back((int)i);
+                        }
+                        for (int i : left)                                  // no free residue: any free lane (that load takes an extra wavefront)
+                            for (int l = 0; l < 32; ++l)
+                                if (lane_piece[l] < 0) { lane_piece[l] = i; lane_start[l] = cl[i].lo; used[l >> 4][l & 15] = true; break; }
+                        for (int l = 0; l < 32; ++l) {
+                            if (lane_piece[l] < 0) { lane_start[l] = l & 15; }  // idle lane: reads its own residue with zero weights
+                            istart[c * 32 + l] = lane_start[l];
+                            if (lane_piece[l] < 0) continue;
+                            const Piece& pc = cl[lane_piece[l]];
+                            seg_slots[pc.seg].push_back(32 * c + l);
+                            for (int j = 0; j < pc.n; ++j) {
+                                const int k = pc.lo + j, sk = seg[k], pp = ioff[c] + (k - lane_start[l]);
+                                iw[((size_t)pp * 32 + l) * 2] = sk >= 1 ? fb_host[(size_t)k * n_mels + sk - 1] : 0.0f;
+                                iw[((size_t)pp * 32 + l) * 2 + 1] = sk < n_mels ? fb_host[(size_t)k * n_mels + sk] : 0.0f;
+                            }
+                        }
+                    }
+                    auto pack = [&](const std::vector<int>& v) {
+                        uint32_t r = 0;
+                        for (int i = 0; i < 4; ++i) r |= (uint32_t)(i < (int)v.size() ? v[i] : 128) << (8 * i);   // 128: the slot kept at zero
+                        return r;
+                    };
+                    for (int m = 0; m < n_mels; ++m) { islot[2 * m] = pack(seg_slots[m]); islot[2 * m + 1] = pack(seg_slots[m + 1]); }
+                }
+            }
+        }
     }
+    if (iw.empty()) iw.assign(64, 0.0f);
     const int gseg_pad = (n_mels + 2 + 3) & ~3;
 
     // ---- twiddles W1024^(ka*j), window * 0.5
@@ -191,7 +287,8 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     const size_t b_tw = tw.size() * 4, b_win = win.size() * 4, b_wt = wt.size() * 4, b_i = (size_t)n_mels_pad * 4;
     const size_t b_wab = wab.size() * 4, b_rm = 32 * 4, b_g0 = 32 * 4, b_gs = (size_t)gseg_pad * 4;
     const size_t b_tw4 = tw4.size() * 4, b_win2 = win2.size() * 4, b_bimg = bimg.size() * 2;
-    const size_t total = b_tw + b_win + b_wt + 3 * b_i + b_wab + b_rm + b_g0 + b_gs + b_tw4 + b_win2 + b_bimg + 16;
+    const size_t b_iw = iw.size() * 4, b_idst = istart.size() * 4, b_islot = islot.size() * 4;
+    const size_t total = b_tw + b_win + b_wt + 3 * b_i + b_wab + b_rm + b_g0 + b_gs + b_tw4 + b_win2 + b_bimg + 16 + b_iw + b_idst + b_islot + 32;
     e = cudaMalloc(&p->blob, total);
     if (e != cudaSuccess) { cudaSetDevice(prev); delete p; return cuda_fail(e); }
     std::vector<unsigned char> host(total, 0);
@@ -210,6 +307,10 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     memcpy(&host[o], win2.data(), b_win2); const size_t o_win2 = o; o += b_win2;
     o = (o + 15) & ~(size_t)15;                                        // the tile image is read as uint4
     memcpy(&host[o], bimg.data(), b_bimg); const size_t o_bimg = o; o += b_bimg;
+    o = (o + 15) & ~(size_t)15;
+    memcpy(&host[o], iw.data(), b_iw); const size_t o_iw = o; o += b_iw;
+    memcpy(&host[o], istart.data(), b_idst); const size_t o_idst = o; o += b_idst;
+    memcpy(&host[o], islot.data(), b_islot); const size_t o_islot = o; o += b_islot;
     e = cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { cudaFree(p->blob); delete p; return cuda_fail(e); }
@@ -232,6 +333,11 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     memcpy(p->mt.chunk, mt_chunk, sizeof(mt_chunk));
     p->dev.gseg_pad = gseg_pad;
     p->dev.fast_ok = fast_ok;
+    p->dev.iw = (const float2*)(d + o_iw);
+    p->dev.istart = (const int*)(d + o_idst);
+    p->dev.islot = (const uint32_t*)(d + o_islot);
+    p->dev.item_ok = item_ok; p->dev.iP = iP; p->dev.iK = iK;
+    for (int c = 0; c < 4; ++c) { p->dev.iL[c] = iL[c]; p->dev.ioff[c] = ioff[c]; }
     p->dev.nnz_pad = (int)wt.size();
     p->dev.n_mels = n_mels; p->dev.n_mels_pad = n_mels_pad;
     p->dev.hop = hop; p->dev.amin = amin < 1.17549435e-38f ? 1.17549435e-38f : amin; p->dev.eps = eps;   // the kernels take log2 of max(v, amin) with a flush-to-zero MUFU: amin below FLT_MIN is raised to it

@@ -25,6 +25,10 @@
 #include "fft32.cuh"
 #include "seld_plan.h"
 
+#ifndef SELD_STRIDED_TILES
+#define SELD_CONTIG 1      // a block owns a contiguous range of tiles (measured -3 % against grid-stride tiles: neighbouring tiles share samples in L1)
+#endif
+
 namespace seld {
 
 #ifdef SELD_PHASE_TIMING
@@ -46,6 +50,7 @@ constexpr int kZeroRun = 127;             // float2 slot of every row kept at (0
 constexpr int kTwStride = 68;             // 32 float2 + pad
 constexpr int kWinStride = 36;            // 32 floats + pad
 constexpr int kXStride = 34;              // exchange buffer row stride in float2 (even: 128-bit reads)
+constexpr int kItemRow = 544;             // item form: float2 per pair-row in natural bin order (513 bins + room to read a class length past the end)
 constexpr int kWabStride = 36;            // floats per lane in the (a, b) weight table: 17 float2 + pad, 36*l mod 32 = 4l
 // Two real channels share each complex transform; splitting the packed spectrum leaves a channel with its partner's
 // rounding noise, about -120 dB relative to the PARTNER (measured: tests/test_imbalance_gpu.py).  A frame in which some
@@ -80,17 +85,27 @@ __device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.f
 // kIV = false: log-mel only (Logmel_Extractor, or channels >= 4 of a wider IV call).  The four transform
 //              slots of a warp then take four consecutive (frame, channel) jobs, j = t * Cj + c with
 //              Cj = C - c_lo channels, so any channel count keeps all four slots busy (C = 1: four frames).
-template <int W, typename TIn, bool kIV, bool kRedo = false>
+// kItem = true: item form of the mel projection (main form of the 4-channel IV kernel).  The packed spectra Z go to shared
+//              memory as they leave the transform, already in the order the mel step reads them: bin k <= 512 into a "P" plane,
+//              bin 1024 - k into an "M" plane at the same place, each at (position, lane) of the piece of its segment that
+//              the plan gave to `lane` (PlanDev::iw / idst).  Lane l then walks its pieces: per position four conflict-free
+//              64-bit loads, the untangle / power / IV arithmetic of that bin (no shuffles: both halves of the conjugate pair
+//              are in the lane) and seven FFMA2 into the sums of the piece.  Every lane runs the same instruction stream, a
+//              piece belongs to one segment, so there are no run boundaries, no predicated partial-sum stores and no
+//              restart multiplies; the band-per-lane combine step reads at most four piece sums per list as before.
+template <int W, typename TIn, bool kIV, bool kRedo = false, bool kItem = false>
 __global__ void __launch_bounds__(W * 32, 1)
 foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
+    static_assert(!kItem || (kIV && !kRedo), "item form: main form of the IV kernel only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // lane-major tables read with 128-bit loads: row stride = 4 (mod 32) words -> conflict-free
     float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: (cos, -sin) of W1024^(lane*brev5(p)), p = 0..31
     float* win_s = tw_s + 32 * kTwStride;                                  // [lane][kWinStride]: window[32*m + lane] * 0.5, m = 0..31
-    float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride
-    int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
-    float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
-    int* marked_s = reinterpret_cast<int*>(R_all + W * kRegion);           // main form: some warp of this block marked a frame
+    float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride          (item form: iw, iP * 32 float2)
+    int* gseg_s = reinterpret_cast<int*>(wab_s + (kItem ? 64 * pd.iP : 32 * kWabStride));   // gseg_pad (item form: none)
+    float* R_all = reinterpret_cast<float*>(gseg_s + (kItem ? 0 : pd.gseg_pad));            // W * region
+    constexpr int region = kItem ? 4 * 2 * kItemRow : kRegion;             // floats per warp (the exchange buffer aliases it)
+    int* marked_s = reinterpret_cast<int*>(R_all + W * region);            // main form: some warp of this block marked a frame
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float in_scale = a.in_scale;
@@ -98,10 +113,19 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     // (kIV: frames; log-mel only: groups of four (frame, channel) jobs), item j = (tile number j / W, warp slot j % W)
     const int redo_Cj = a.C - a.c_lo;
     const int64_t redo_J = (int64_t)a.T * redo_Cj;                          // log-mel only: jobs per clip
+#ifdef SELD_CONTIG
+    const int redo_t0 = kRedo ? (int)(((int64_t)a.redo_block * a.n_tiles) / a.redo_grid) : 0;
+    const int redo_tiles = kRedo ? (int)(((int64_t)(a.redo_block + 1) * a.n_tiles) / a.redo_grid) - redo_t0 : 0;
+#else
     const int redo_tiles = (kRedo && a.n_tiles > a.redo_block) ? (a.n_tiles - 1 - a.redo_block) / a.redo_grid + 1 : 0;
+#endif
     const int redo_items = redo_tiles * W;
     auto redo_item = [&](int j, int& b, int& grp) -> bool {                 // false: no such frame / group
+#ifdef SELD_CONTIG
+        const int tile = redo_t0 + j / W;
+#else
         const int tile = a.redo_block + (j / W) * a.redo_grid;
+#endif
         b = tile / a.tiles_per_clip;
         grp = (tile - b * a.tiles_per_clip) * W + (j % W);
         return kIV ? grp < a.T : (int64_t)4 * grp < redo_J;
@@ -129,12 +153,17 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         tw_s[l * kTwStride + 2 * r] = w.x; tw_s[l * kTwStride + 2 * r + 1] = w.y;
         win_s[l * kWinStride + r] = pd.win[i] * in_scale;                   // int16 PCM: the 2^-15 of soundfile's conversion, exact
     }
-    for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
-    for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
+    if constexpr (kItem) {
+        for (int i = tid; i < 64 * pd.iP; i += W * 32) wab_s[i] = reinterpret_cast<const float*>(pd.iw)[i];
+        for (int i = tid; i < W * region; i += W * 32) R_all[i] = 0.0f;     // the entries behind bin 512 are read with zero weights: keep them finite
+    } else {
+        for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
+        for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
+    }
     if (tid == 0) *marked_s = 0;
     __syncthreads();
 
-    float* R = R_all + warp * kRegion;
+    float* R = R_all + warp * region;
     float2* scratch = reinterpret_cast<float2*>(R);
     const uint32_t runmask = pd.runmask[lane];
     const int g0 = pd.g0[lane];
@@ -159,11 +188,24 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     };
     constexpr uint32_t kNoRuns = kZeroRun * 0x01010101u;
     uint32_t slotV0 = kNoRuns, slotU0 = kNoRuns, slotV1 = kNoRuns, slotU1 = kNoRuns;
-    if (lane < M) { slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]); slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]); }
-    if (lane + 32 < M) { slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]); slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]); }
+    int ist[4] = {0, 0, 0, 0};                                             // item form: first bin this lane reads in class c
+    if constexpr (kItem) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ist[c] = pd.istart[c * 32 + lane];
+    }
+    constexpr int kItemZero = 128, kItemSlots = 136;                       // item form: slot kept at zero, slots per array (4 classes x 32 lanes + zero + pad)
+    if constexpr (kItem) {
+        slotV0 = slotU0 = slotV1 = slotU1 = kItemZero * 0x01010101u;
+        if (lane < M) { slotV0 = pd.islot[2 * lane]; slotU0 = pd.islot[2 * lane + 1]; }
+        if (lane + 32 < M) { slotV1 = pd.islot[2 * (lane + 32)]; slotU1 = pd.islot[2 * (lane + 32) + 1]; }
+    } else {
+        if (lane < M) { slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]); slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]); }
+        if (lane + 32 < M) { slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]); slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]); }
+    }
     // fourth slot in use by any band?  (warp-uniform; most banks never split a segment over four chunks)
-    const bool four = __any_sync(0xffffffffu, (slotV0 >> 24) != kZeroRun || (slotU0 >> 24) != kZeroRun ||
-                                              (slotV1 >> 24) != kZeroRun || (slotU1 >> 24) != kZeroRun);
+    constexpr uint32_t kAbsent = kItem ? kItemZero : kZeroRun;
+    const bool four = __any_sync(0xffffffffu, (slotV0 >> 24) != kAbsent || (slotU0 >> 24) != kAbsent ||
+                                              (slotV1 >> 24) != kAbsent || (slotU1 >> 24) != kAbsent);
 
 #ifdef SELD_PHASE_TIMING
     long long phase_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -178,7 +220,11 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         // ---------------- mel step 1: chunk walk of all rows, per-run partial sums (U, V) left in the rows
         constexpr int NR = kIV ? kRows : 4;
         constexpr int NP = kIV ? kPairs : 2;                                // pair-rows in use
-        {
+#ifndef ABL_NOWALK
+        // the walk handles NPP pair-rows at a time: all of them in the 255-register builds, two at a time where registers
+        // are scarce (W > 8: 168 registers per thread)
+        auto walk_pairs = [&](auto f0_c, auto npp_c) {
+            constexpr int F0 = decltype(f0_c)::value, NPP = decltype(npp_c)::value;
             float2 wv[17];
             const float4* wp = reinterpret_cast<const float4*>(wab_s + lane * kWabStride);
 #pragma unroll
@@ -188,10 +234,10 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 wv[2 * i + 1] = make_float2(v.z, v.w);
             }
             wv[16] = *reinterpret_cast<const float2*>(wab_s + lane * kWabStride + 32);
-            float2 q[NP][17];                                               // (row, row') values of the lane's 16 (+1) bins
+            float2 q[NPP][17];                                              // (row, row') values of the lane's 16 (+1) bins
 #pragma unroll
-            for (int f = 0; f < NP; ++f) {
-                const float* row = R + f * kPairWords;
+            for (int f = 0; f < NPP; ++f) {
+                const float* row = R + (F0 + f) * kPairWords;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float4 v = *reinterpret_cast<const float4*>(row + 32 * lane + 4 * (i ^ (lane & 7)));
@@ -201,15 +247,15 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             }
             __syncwarp();                                                   // everyone holds its bins: rows may be overwritten
             PHASE_MARK(9);   // walk: weights + rows in registers
-            if (lane < NP) reinterpret_cast<float4*>(R + lane * kPairWords)[kZeroRun] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < NPP) reinterpret_cast<float4*>(R + (F0 + lane) * kPairWords)[kZeroRun] = make_float4(0.f, 0.f, 0.f, 0.f);
             // per pair-row: U = sum a_k q_k and V = sum b_k q_k of the current run, each for both rows of the pair
-            float2 U[NP], V[NP];
-            float2* po = reinterpret_cast<float2*>(R) + 2 * g0;             // slot of run r: words 4r..4r+3 = (U, U', V, V'), two 64-bit stores
+            float2 U[NPP], V[NPP];
+            float2* po = reinterpret_cast<float2*>(R + F0 * kPairWords) + 2 * g0;   // slot of run r: words 4r..4r+3 = (U, U', V, V'), two 64-bit stores
                                                                             // (one 128-bit store would need the four values moved into an aligned register quad)
             {
                 const float2 aa = make_float2(wv[0].x, wv[0].x), bb = make_float2(wv[0].y, wv[0].y);
 #pragma unroll
-                for (int f = 0; f < NP; ++f) { U[f] = __fmul2_rn(aa, q[f][0]); V[f] = __fmul2_rn(bb, q[f][0]); }
+                for (int f = 0; f < NPP; ++f) { U[f] = __fmul2_rn(aa, q[f][0]); V[f] = __fmul2_rn(bb, q[f][0]); }
             }
             // branch-free: where a new run starts the finished sums are stored and the accumulators restart
             // (acc * keep with keep = 0); the weights are broadcast once per bin for all rows
@@ -220,7 +266,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 const float2 kk = make_float2(keep, keep);
                 const float2 aa = make_float2(wv[j].x, wv[j].x), bb = make_float2(wv[j].y, wv[j].y);
 #pragma unroll
-                for (int f = 0; f < NP; ++f) {
+                for (int f = 0; f < NPP; ++f) {
                     if (start) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
                     U[f] = __ffma2_rn(aa, q[f][j], __fmul2_rn(U[f], kk));
                     V[f] = __ffma2_rn(bb, q[f][j], __fmul2_rn(V[f], kk));
@@ -228,11 +274,21 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 po += start ? 2 : 0;
             });
 #pragma unroll
-            for (int f = 0; f < NP; ++f) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
+            for (int f = 0; f < NPP; ++f) { po[f * (kPairWords / 2)] = U[f]; po[f * (kPairWords / 2) + 1] = V[f]; }
+        };
+        if constexpr (kItem) {
+            // the piece sums are in place already (main loop)
+        } else if constexpr (W > 8 && NP == 4) {
+            walk_pairs(std::integral_constant<int, 0>{}, std::integral_constant<int, 2>{});
+            walk_pairs(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+        } else {
+            walk_pairs(std::integral_constant<int, 0>{}, std::integral_constant<int, NP>{});
         }
+#endif
         __syncwarp();
 
         PHASE_MARK(7);   // mel walk
+#ifndef ABL_NOCOMB
         // ---------------- mel step 2: band per lane, out[m] = sum V(runs of segment m) + sum U(runs of segment m+1)
         {
             // destination of row f (one 64-float line of the output per row): kIV: channels 0-3 and the three
@@ -269,18 +325,37 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                         if (m < M) {
                             const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
                             float2 vv[NP];                                  // both rows of a pair per packed add
+                            if constexpr (kItem) {
+                                // piece sums: arrays [U pair 0 | V pair 0 | U 1 | V 1 | U 2 | V 2 | (U, V) of n2], kItemSlots float2 each
+                                const float2* S = reinterpret_cast<const float2*>(R);
+                                const int iv0 = pv & 0xff, iv1 = (pv >> 8) & 0xff, iv2 = (pv >> 16) & 0xff, iv3 = pv >> 24;
+                                const int iu0 = pu & 0xff, iu1 = (pu >> 8) & 0xff, iu2 = (pu >> 16) & 0xff, iu3 = pu >> 24;
 #pragma unroll
-                            for (int f = 0; f < NP; ++f) {
-                                const float2* rowp = reinterpret_cast<const float2*>(R + f * kPairWords);   // slot r: [2r] = U pair, [2r+1] = V pair
-                                const float2 v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
-                                const float2 v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
-                                const float2 u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
-                                const float2 u2 = rowp[2 * ((pu >> 16) & 0xff)];
-                                if constexpr (kFour) {
-                                    const float2 v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
-                                    vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, v3)), vadd(vadd(u0, u1), vadd(u2, u3)));
-                                } else {
-                                    vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
+                                for (int f = 0; f < 3; ++f) {
+                                    const float2* su = S + (2 * f) * kItemSlots;
+                                    const float2* sv = su + kItemSlots;
+                                    const float2 v0 = sv[iv0], v1 = sv[iv1], v2 = sv[iv2], u0 = su[iu0], u1 = su[iu1], u2 = su[iu2];
+                                    if constexpr (kFour) vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, sv[iv3])), vadd(vadd(u0, u1), vadd(u2, su[iu3])));
+                                    else vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
+                                }
+                                const float2* s3 = S + 6 * kItemSlots;
+                                float t3 = ((s3[iv0].y + s3[iv1].y) + s3[iv2].y) + ((s3[iu0].x + s3[iu1].x) + s3[iu2].x);
+                                if constexpr (kFour) t3 += s3[iv3].y + s3[iu3].x;
+                                vv[3] = make_float2(t3, 0.0f);
+                            } else {
+#pragma unroll
+                                for (int f = 0; f < NP; ++f) {
+                                    const float2* rowp = reinterpret_cast<const float2*>(R + f * kPairWords);   // slot r: [2r] = U pair, [2r+1] = V pair
+                                    const float2 v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
+                                    const float2 v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
+                                    const float2 u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
+                                    const float2 u2 = rowp[2 * ((pu >> 16) & 0xff)];
+                                    if constexpr (kFour) {
+                                        const float2 v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
+                                        vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, v3)), vadd(vadd(u0, u1), vadd(u2, u3)));
+                                    } else {
+                                        vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
+                                    }
                                 }
                             }
                             float v[NR];
@@ -324,11 +399,25 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 }
             }
         }
+#endif
         return bad;
     };
 
     // tile = (clip tb, tile tr within the clip), advanced by the grid size without a division per frame (the
     // division was a 500-cycle dependent chain at the top of every frame)
+#ifdef SELD_CONTIG
+    // a block owns a contiguous range of tiles: consecutive tiles of a clip share 1024 - hop samples per frame, which the
+    // block then finds in its L1 instead of fetching every tile cold from L2
+    const int tile_lo = (int)(((int64_t)blockIdx.x * a.n_tiles) / gridDim.x);
+    int tiles_left = (int)(((int64_t)(blockIdx.x + 1) * a.n_tiles) / gridDim.x) - tile_lo;
+    int tb = tile_lo / a.tiles_per_clip, tr = tile_lo - tb * a.tiles_per_clip;
+    auto next_tile = [&]() {
+        --tiles_left; ++tr;
+        if (tr >= a.tiles_per_clip) { tr = 0; ++tb; }
+    };
+    if constexpr (!kRedo) {
+    for (; tiles_left > 0; next_tile()) {
+#else
     int tb = blockIdx.x / a.tiles_per_clip, tr = blockIdx.x - tb * a.tiles_per_clip;
     auto next_tile = [&]() {
         tb += a.step_clip; tr += a.step_tile;
@@ -336,6 +425,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     };
     if constexpr (!kRedo) {
     for (; tb < a.B; next_tile()) {
+#endif
         const int b = tb;
         const int grp = tr * W + warp;                                      // kIV: the frame; else: group of 4 jobs
         int tk[4] = {0, 0, 0, 0}, ck[4] = {0, 0, 0, 0};                     // log-mel only: frame / channel of each transform slot
@@ -362,6 +452,16 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         // ---------------- load + window: re = (slot 0, slot 2), im = (slot 1, slot 3)
         if constexpr (kIV) {                                                // slots = channels 0-3 of frame t
             const int64_t s0 = (int64_t)t * hop - 512;
+#ifdef ABL_NOLOAD
+            if (true) {
+                static_for<0, 32>([&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    const float v = (float)(lane + t) * 1e-3f + (float)m;
+                    re[m] = make_float2(v, v + 1.0f);
+                    im[m] = make_float2(v + 2.0f, v + 3.0f);
+                });
+            } else
+#endif
             if (s0 >= 0 && s0 + 1024 <= a.L) {
                 const TIn* p0 = xb + s0 + lane;
                 const TIn* p1 = p0 + a.stride_c;
@@ -416,6 +516,17 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             }
         }
         PHASE_MARK(1);   // loads issued
+#ifdef SELD_PREFETCH_L1
+        if constexpr (kIV) {
+            // the hop of new samples this warp's next frame (t + W) adds to what the block has touched: one line per lane
+            const int64_t pf = (int64_t)(t + W) * hop + 512 - hop + (lane & 7) * (128 / (int)sizeof(TIn));
+            if (t + W < a.T && pf < a.L) {
+                const TIn* pp = xb + (lane >> 3) * a.stride_c + pf;
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(pp));
+            }
+        }
+#endif
+#ifndef ABL_NOWIN
         static_for<0, 8>([&](auto mi) {
             constexpr int m4 = decltype(mi)::value;
             const float4 w4 = *reinterpret_cast<const float4*>(win_s + lane * kWinStride + 4 * m4);
@@ -426,11 +537,15 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 im[4 * m4 + e] = vmuls(im[4 * m4 + e], w[e]);
             }
         });
+#endif
 
         PHASE_MARK(2);   // loads landed + window
         // ---------------- two 1024-point FFTs at once: 32-pt, twiddle, exchange, 32-pt
+#ifndef ABL_NOFFT1
         fft32(re, im);
+#endif
         PHASE_MARK(3);   // first 32-pt
+#ifndef ABL_NOTW
         static_for<0, 16>([&](auto pi) {
             constexpr int p2 = decltype(pi)::value;                         // positions 2*p2, 2*p2+1
             const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
@@ -443,6 +558,8 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             re[2 * p2 + 1] = vfmas(i, -w4.w, vmuls(r, w4.z));
             im[2 * p2 + 1] = vfmas(i, w4.z, vmuls(r, w4.w));
         });
+#endif
+#ifndef ABL_NOEXCH
         static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = re[p]; });
         __syncwarp();
         static_for<0, 16>([&](auto ji) {
@@ -459,8 +576,11 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             im[2 * j] = make_float2(v.x, v.y); im[2 * j + 1] = make_float2(v.z, v.w);
         });
         __syncwarp();
+#endif
         PHASE_MARK(4);   // twiddle + exchange
+#ifndef ABL_NOFFT2
         fft32(re, im);                                                      // position p: Z[lane + 32*brev5(p)]
+#endif
         PHASE_MARK(5);   // second 32-pt
 
         // ---------------- per-bin quantities -> 7 rows
@@ -472,6 +592,12 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 constexpr int p = brev5(kb & 31);
                 const float2 zr = re[p], zi = im[p];
                 float2 pr, pi;
+#ifdef ABL_NOSHFL
+                if constexpr (true) {
+                    constexpr int pp = brev5(31 - (kb & 15));
+                    pr = re[pp]; pi = im[pp];
+                } else
+#endif
                 if constexpr (kb == 16) {
                     pr = zr; pi = zi;
                 } else {
@@ -491,14 +617,23 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                     const float2 i13 = vfmas(bi, ai.x, vmuls(br, ar.x));    // Re(conj(X0) X1), Re(conj(X0) X3)
                     const float i2 = fmaf(ai.x, ai.y, ar.x * ar.y);         // Re(conj(X0) X2)
                     const float s = fmaf(i13.y, i13.y, fmaf(i2, i2, i13.x * i13.x));
+#ifdef ABL_NOMUFU
+                    const float inv = s + eps;
+#else
                     const float nrm = sqrt_ftz(s) + eps;                     // one MUFU; sqrt(0) = 0, subnormal sums flush to 0 (far below eps)
                     const float inv = rcp_ftz(nrm);
+#endif
+#ifdef ABL_NOROWST
+                    if (__float_as_uint(p02.x + p13.x + i13.x * inv + i2 * inv + p02.y + p13.y + i13.y) == 0x12345678u) {
+#else
                     if (kb < 16 || lane == 0) {
-                        float2* q = reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
-                        q[0 * (kPairWords / 2)] = p02;
-                        q[1 * (kPairWords / 2)] = p13;
-                        q[2 * (kPairWords / 2)] = vmuls(i13, inv);
-                        q[3 * (kPairWords / 2)] = make_float2(i2 * inv, 0.0f);
+#endif
+                        constexpr int kPS = kItem ? kItemRow : kPairWords / 2;            // float2 per pair-row
+                        float2* q = kItem ? reinterpret_cast<float2*>(R) + 32 * kb + lane : reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
+                        q[0 * kPS] = p02;
+                        q[1 * kPS] = p13;
+                        q[2 * kPS] = vmuls(i13, inv);
+                        q[3 * kPS] = make_float2(i2 * inv, 0.0f);
                     }
                 } else {
                     if (kb < 16 || lane == 0) {
@@ -510,6 +645,48 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             });
         }
         __syncwarp();
+        if constexpr (kItem) {
+            // ---------------- item form of the mel step: every lane walks its pieces (one per class) through the rows
+            PHASE_MARK(6);   // pointwise
+            float2 aU[4][3], aV[4][3], a3[4];                               // piece sums per class: three row pairs (U, V), and (U, V) of n2
+            const float2* const iw_s = reinterpret_cast<const float2*>(wab_s);
+            const float2* const Q = reinterpret_cast<const float2*>(R);
+            static_for<0, 4>([&](auto ci) {
+                constexpr int c = decltype(ci)::value;
+#pragma unroll
+                for (int f = 0; f < 3; ++f) { aU[c][f] = make_float2(0.0f, 0.0f); aV[c][f] = make_float2(0.0f, 0.0f); }
+                a3[c] = make_float2(0.0f, 0.0f);
+                const int Lc = pd.iL[c];
+                const float2* qp = Q + ist[c];
+                const float2* wp = iw_s + 32 * pd.ioff[c] + lane;
+#pragma unroll 4
+                for (int j = 0; j < Lc; ++j, ++qp, wp += 32) {
+                    const float2 q0 = qp[0], q1 = qp[kItemRow], q2 = qp[2 * kItemRow], q3 = qp[3 * kItemRow];
+                    const float2 w = *wp;
+                    const float2 aa = make_float2(w.x, w.x), bb = make_float2(w.y, w.y);
+                    aU[c][0] = __ffma2_rn(aa, q0, aU[c][0]); aV[c][0] = __ffma2_rn(bb, q0, aV[c][0]);
+                    aU[c][1] = __ffma2_rn(aa, q1, aU[c][1]); aV[c][1] = __ffma2_rn(bb, q1, aV[c][1]);
+                    aU[c][2] = __ffma2_rn(aa, q2, aU[c][2]); aV[c][2] = __ffma2_rn(bb, q2, aV[c][2]);
+                    a3[c] = __ffma2_rn(w, make_float2(q3.x, q3.x), a3[c]);
+                }
+            });
+            __syncwarp();                                                   // every lane is through with the rows: the sums may overwrite them
+            PHASE_MARK(9);   // piece walk
+            float2* const S = reinterpret_cast<float2*>(R);
+            static_for<0, 4>([&](auto ci) {
+                constexpr int c = decltype(ci)::value;
+                if (c < pd.iK) {
+#pragma unroll
+                    for (int f = 0; f < 3; ++f) {
+                        S[(2 * f) * kItemSlots + 32 * c + lane] = aU[c][f];
+                        S[(2 * f + 1) * kItemSlots + 32 * c + lane] = aV[c][f];
+                    }
+                    S[6 * kItemSlots + 32 * c + lane] = a3[c];
+                }
+            });
+            if (lane < 7) S[lane * kItemSlots + kItemZero] = make_float2(0.0f, 0.0f);
+            __syncwarp();
+        }
 
         const bool bad = mel_rows(std::true_type{}, b, t, tk, ck, vk);
         if (__any_sync(0xffffffffu, bad) && lane == 0) {                    // lane 0 also wrote element 0 of every row: program order
@@ -676,14 +853,19 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 // ---------------------------------------------------------------------------------------------
 template <int W>
 static size_t iv2_smem_bytes(const PlanDev& pd) {
-    return (size_t)(32 * kTwStride + 32 * kWinStride + 32 * kWabStride + pd.gseg_pad + W * kRegion + 4) * sizeof(float);
+#ifndef SELD_SMEM_PAD
+#define SELD_SMEM_PAD 0
+#endif
+    return (size_t)(32 * kTwStride + 32 * kWinStride + 32 * kWabStride + pd.gseg_pad + W * kRegion + 4) * sizeof(float) + SELD_SMEM_PAD;
 }
 
 // Warps (= frames) per block.  One block per SM; more warps hide latency, fewer leave more
 // registers per thread (8 -> 255, 12 -> 168; warps are allocated in fours).  Measured at cfg2: 8 -> 0.46 ms,
 // 12 (spills) -> 0.51 ms; the 12-warp build only exists under -DSELD_EXPERIMENTS (SELD_IV2_WARPS=12).
 static int iv2_warps() {
-#ifdef SELD_EXPERIMENTS
+#ifdef SELD_IV2_W
+    return SELD_IV2_W;
+#elif defined(SELD_EXPERIMENTS)
     static int w = [] {
         const char* e = getenv("SELD_IV2_WARPS");
         const int v = e ? atoi(e) : 8;
@@ -696,21 +878,26 @@ static int iv2_warps() {
 }
 
 bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin) {
-    return pd.fast_ok && iv2_smem_bytes<12>(pd) <= smem_optin;
+    return pd.fast_ok && iv2_smem_bytes<12>(pd) - SELD_SMEM_PAD <= smem_optin;
 }
 
 int foa_iv2_frames_per_tile() { return iv2_warps(); }
 
-template <int W, typename TIn, bool kIV>
+static size_t iv2_item_smem_bytes(const PlanDev& pd, int W) {
+    return (size_t)(32 * kTwStride + 32 * kWinStride + 64 * pd.iP + W * 4 * 2 * kItemRow + 4) * sizeof(float);
+}
+
+template <int W, typename TIn, bool kIV, bool kItem = false>
 static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
-    const size_t smem = iv2_smem_bytes<W>(pd);
+    const size_t smem_redo = iv2_smem_bytes<W>(pd);                         // the redo form always runs the run form of the mel step
+    const size_t smem = kItem ? iv2_item_smem_bytes(pd, W) : smem_redo;
     static std::atomic<uint64_t> attr_done{0};                              // per device, once per process and instantiation
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     const uint64_t bit = 1ull << (dev & 63);
     if (!(attr_done.load(std::memory_order_relaxed) & bit)) {
-        e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV, false, kItem>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(foa_iv2_kernel<W, TIn, kIV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
@@ -719,8 +906,8 @@ static cudaError_t iv2_launch_t(const FoaArgs& a, const PlanDev& pd, int sm_coun
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
     FoaArgs aa = a;
     aa.step_clip = gx / a.tiles_per_clip; aa.step_tile = gx - aa.step_clip * a.tiles_per_clip;
-    aa.smem_bytes = (int)smem;                                              // blocks that mark frames launch the redo form themselves
-    foa_iv2_kernel<W, TIn, kIV><<<gx, W * 32, smem, st>>>(aa, pd);
+    aa.smem_bytes = (int)smem_redo;                                         // blocks that mark frames launch the redo form themselves
+    foa_iv2_kernel<W, TIn, kIV, false, kItem><<<gx, W * 32, smem, st>>>(aa, pd);
     return cudaGetLastError();
 }
 
@@ -733,6 +920,16 @@ extern "C" void seld_dev_phase_cycles(unsigned long long* out, int reset) {
 #endif
 
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
+#ifdef SELD_IV2_W
+    if (a.in_i16) return iv2_launch_t<SELD_IV2_W, int16_t, true>(a, pd, sm_count, st);
+    return iv2_launch_t<SELD_IV2_W, float, true>(a, pd, sm_count, st);
+#endif
+#ifndef SELD_NO_ITEM
+    if (pd.item_ok && iv2_item_smem_bytes(pd, 8) <= 227 * 1024) {           // item form of the mel step (the default for every bank it fits)
+        if (a.in_i16) return iv2_launch_t<8, int16_t, true, true>(a, pd, sm_count, st);
+        return iv2_launch_t<8, float, true, true>(a, pd, sm_count, st);
+    }
+#endif
     if (a.in_i16) return iv2_launch_t<8, int16_t, true>(a, pd, sm_count, st);   // PCM input: always the 8-warp build (frames_per_tile says 8 then, too)
 #ifdef SELD_EXPERIMENTS
     if (iv2_warps() == 12) return iv2_launch_t<12, float, true>(a, pd, sm_count, st);

@@ -23,6 +23,15 @@ struct PlanDev {
     const uint32_t* runmask;  // [32] bit j: a new run (segment change) starts at the lane's bin j
     const int* g0;        // [32] index of the lane's first run
     const int* gseg;      // [n_mels + 2] first run of segment s; runs of s are [gseg[s], gseg[s+1])
+    // item form of the bank for the iv2 kernel's main path (valid when item_ok): every segment is cut into pieces of at most
+    // iL[class] bins; lane l works through one piece per class (positions ioff[c] .. ioff[c] + iL[c], read from bins
+    // istart[c][l] + j of the rows), so all lanes share one instruction stream with no run boundaries inside it (outside its
+    // piece a lane's weights are zero)
+    const float2* iw;     // [iP][32] (a, b) of position p of lane l
+    const int* istart;    // [4 classes][32 lanes] first bin lane l reads in class c
+    const uint32_t* islot;// [n_mels][2] slot lists, 4 x 8 bits each: pieces of segment m (their V sums) and of segment m + 1 (U sums)
+    int item_ok, iP, iK;
+    int iL[4], ioff[4];
     int gseg_pad;         // ints reserved for gseg in shared memory (multiple of 4)
     int fast_ok;          // bank has the segment structure and the run table fits
     int nnz_pad;          // floats in wt (multiple of 4)

@@ -4,13 +4,9 @@ iv2 kernel spends its cycles (clock64 per phase, averaged per frame).  Run on th
 import ctypes, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from pseldnets_b200 import build as b
-lib_path = os.path.join(ROOT, 'gpurun_out', 'libseldfeat_timing.so')
-os.makedirs(os.path.dirname(lib_path), exist_ok=True)
-cmd = ['nvcc'] + b.NVCC_FLAGS + ['-DSELD_PHASE_TIMING', '-o', lib_path] + [os.path.join(b.CSRC, s) for s in b.SOURCES]
-subprocess.check_call(cmd)
+# the timing build is made where nvcc is (tools/build_variant.sh out.so seld_foa_iv2.cu -DSELD_PHASE_TIMING) and passed in SELD_LIB
 from pseldnets_b200 import _abi
-_abi.LIB_PATH = lib_path
+assert 'SELD_LIB' in os.environ, 'SELD_LIB=<timing build> python tools/tools_phase_timing.py'
 import torch
 import pseldnets_b200 as pb
 cfg = {'data': {'sample_rate': 24000, 'nfft': 1024, 'hoplen': 240, 'n_mels': 64, 'window': 'hann', 'audio_feature': 'logmelIV'}}
