@@ -2,11 +2,13 @@
 // the per-call argument checks + launches.  See include/seldfeat.h for the contract.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <new>
 #include <vector>
 
@@ -134,7 +136,48 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                 const float wa = sk >= 1 ? fb_host[(size_t)k * n_mels + sk - 1] : 0.0f, wb = sk < n_mels ? fb_host[(size_t)k * n_mels + sk] : 0.0f;
                 if (wa != 0.0f || wb != 0.0f) { if (k < slo[sk]) slo[sk] = k; shi[sk] = k; }
             }
-            std::vector<Piece> best; int bestK = 0; long bestCost = -1;
+            // Placement of one class: lane l reads bins start[l] + j, j < L, of the rows (natural bin order) with weight zero
+            // outside its piece.  A warp-wide 64-bit load is two half-warp requests, each conflict-free when its 16 lanes start
+            // at 16 different residues mod 16; a piece shorter than L may start up to L - n bins early, which is what makes the
+            // residues assignable: maximum bipartite matching pieces <-> (half-warp, residue) = lane (Kuhn's augmenting paths).
+            struct Place { int piece[32], start[32], wf; };
+            auto place_class = [&](const std::vector<Piece>& cl, int L) {
+                Place pl;
+                for (int l = 0; l < 32; ++l) { pl.piece[l] = -1; pl.start[l] = l & 15; }   // idle lane: reads its own residue with zero weights
+                std::vector<std::vector<int>> adj(cl.size());                              // adj[i]: starts piece i may take
+                for (size_t i = 0; i < cl.size(); ++i)
+                    for (int d = 0; d <= L - cl[i].n && d <= cl[i].lo; ++d)
+                        if (cl[i].lo - d + L <= F) adj[i].push_back(cl[i].lo - d);         // a lane never reads past bin 512
+                std::vector<int> start_of(cl.size(), -1);
+                std::vector<char> seen;
+                std::function<bool(int)> augment = [&](int i) -> bool {
+                    for (int st : adj[i])
+                        for (int h = 0; h < 2; ++h) {
+                            const int l = 16 * h + (st & 15);
+                            if (seen[l]) continue;
+                            seen[l] = 1;
+                            if (pl.piece[l] < 0 || augment(pl.piece[l])) { pl.piece[l] = i; pl.start[l] = st; start_of[i] = st; return true; }
+                        }
+                    return false;
+                };
+                std::vector<int> order(cl.size());
+                for (size_t i = 0; i < cl.size(); ++i) order[i] = (int)i;
+                std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return adj[x].size() < adj[y].size(); });
+                std::vector<int> left;
+                for (int i : order) { seen.assign(32, 0); if (adj[i].empty() || !augment(i)) left.push_back(i); }
+                for (int i : left)                                          // no residue left for it: any free lane (those loads take an extra wavefront)
+                    for (int l = 0; l < 32; ++l)
+                        if (pl.piece[l] < 0) { pl.piece[l] = i; pl.start[l] = std::max(0, std::min(cl[i].lo, F - L)); break; }
+                pl.wf = 0;
+                for (int h = 0; h < 2; ++h) {
+                    int cnt[16] = {}, mx = 0;
+                    for (int l = 16 * h; l < 16 * h + 16; ++l) mx = std::max(mx, ++cnt[pl.start[l] & 15]);
+                    pl.wf += mx;
+                }
+                return pl;
+            };
+            // Search: classes K, longest piece `maxlen`, and `slack` extra positions per class (more freedom for the matching)
+            std::vector<Piece> best; int bestK = 0, bestSlack = 0; long bestCost = -1;
             for (int K = 1; K <= 4; ++K)
                 for (int maxlen = 1; maxlen <= 24; ++maxlen) {
                     std::vector<Piece> pc; bool ok = true;
@@ -147,52 +190,40 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                     }
                     if (!ok || (int)pc.size() > 32 * K || pc.empty()) continue;
                     std::stable_sort(pc.begin(), pc.end(), [](const Piece& x, const Piece& y) { return x.n > y.n; });
-                    int P = 0;
-                    for (int c = 0; c < K; ++c) if ((size_t)(32 * c) < pc.size()) P += pc[32 * c].n;
-                    const long cost = 14L * P + 20L * K;
-                    if (bestCost < 0 || cost < bestCost) { bestCost = cost; best = pc; bestK = K; }
+                    for (int slack = 0; slack <= 2; ++slack) {
+                        long cost = 28L * K; int P = 0;
+                        for (int c = 0; c < K; ++c) {
+                            if ((size_t)(32 * c) >= pc.size()) continue;
+                            std::vector<Piece> cl(pc.begin() + 32 * c, pc.begin() + std::min(pc.size(), (size_t)32 * (c + 1)));
+                            const int L = cl[0].n + slack;
+                            const Place pl = place_class(cl, L);
+                            cost += (long)L * (7 * pl.wf + 12) / 2;    // per position: 3.5 loads of pl.wf wavefronts, the weights, the arithmetic
+                            P += L;
+                        }
+                        if (P > 24) continue;
+                        if (bestCost < 0 || cost < bestCost) { bestCost = cost; best = pc; bestK = K; bestSlack = slack; }
+                    }
                 }
             if (bestCost >= 0) {
                 iK = bestK;
-                for (int c = 0; c < 4; ++c) { iL[c] = (c < iK && (size_t)(32 * c) < best.size()) ? best[32 * c].n : 0; }
+                for (int c = 0; c < 4; ++c) { iL[c] = (c < iK && (size_t)(32 * c) < best.size()) ? best[32 * c].n + bestSlack : 0; }
                 for (int c = 0; c < 4; ++c) { ioff[c] = iP; iP += iL[c]; }
                 if (iP >= 8 && iP <= 24) {
                     item_ok = 1;
-                    // Placement: lane l reads positions ioff[c] .. ioff[c] + iL[c] of class c from bins istart[c][l] + j of the
-                    // rows (natural bin order), with weight zero outside its piece.  A warp-wide 64-bit load is conflict-free
-                    // when the 16 lanes of each half-warp start at 16 different residues mod 16; a piece shorter than its
-                    // class may start up to iL[c] - n bins early, which is what makes the residues assignable.
                     iw.assign((size_t)iP * 32 * 2, 0.0f);
                     std::vector<std::vector<int>> seg_slots(n_mels + 2);
                     for (int c = 0; c < iK; ++c) {
+                        if (iL[c] == 0) continue;
                         std::vector<Piece> cl(best.begin() + std::min(best.size(), (size_t)32 * c), best.begin() + std::min(best.size(), (size_t)32 * (c + 1)));
-                        int lane_piece[32], lane_start[32];
-                        bool used[2][16] = {};
-                        for (int l = 0; l < 32; ++l) { lane_piece[l] = -1; lane_start[l] = -1; }
-                        std::vector<int> left;
-                        for (size_t i = 0; i < cl.size(); ++i) {             // longest (least freedom) first: cl is sorted by length
-                            bool placed = false;
-                            for (int d = 0; d <= iL[c] - cl[i].n && d <= cl[i].lo && !placed; ++d) {
-                                const int st = cl[i].lo - d, r = st & 15;
-                                for (int h = 0; h < 2 && !placed; ++h) {
-                                    if (used[h][r]) continue;
-                                    const int l = 16 * h + r;              // lane = residue inside its half-warp
-                                    used[h][r] = true; lane_piece[l] = (int)i; lane_start[l] = st; placed = true;
-                                }
-                            }
-                            if (!placed) left.push_back((int)i);
-                        }
-                        for (int i : left)                                  // no free residue: any free lane (that load takes an extra wavefront)
-                            for (int l = 0; l < 32; ++l)
-                                if (lane_piece[l] < 0) { lane_piece[l] = i; lane_start[l] = cl[i].lo; used[l >> 4][l & 15] = true; break; }
+                        const Place pl = place_class(cl, iL[c]);
+                        if (getenv("SELD_PLAN_DEBUG")) fprintf(stderr, "[seld plan] class %d: %d positions, %zu pieces, %d wavefronts per 64-bit load\n", c, iL[c], cl.size(), pl.wf);
                         for (int l = 0; l < 32; ++l) {
-                            if (lane_piece[l] < 0) { lane_start[l] = l & 15; }  // idle lane: reads its own residue with zero weights
-                            istart[c * 32 + l] = lane_start[l];
-                            if (lane_piece[l] < 0) continue;
-                            const Piece& pc = cl[lane_piece[l]];
+                            istart[c * 32 + l] = pl.start[l];
+                            if (pl.piece[l] < 0) continue;
+                            const Piece& pc = cl[pl.piece[l]];
                             seg_slots[pc.seg].push_back(32 * c + l);
                             for (int j = 0; j < pc.n; ++j) {
-                                const int k = pc.lo + j, sk = seg[k], pp = ioff[c] + (k - lane_start[l]);
+                                const int k = pc.lo + j, sk = seg[k], pp = ioff[c] + (k - pl.start[l]);
                                 iw[((size_t)pp * 32 + l) * 2] = sk >= 1 ? fb_host[(size_t)k * n_mels + sk - 1] : 0.0f;
                                 iw[((size_t)pp * 32 + l) * 2 + 1] = sk < n_mels ? fb_host[(size_t)k * n_mels + sk] : 0.0f;
                             }

@@ -51,6 +51,9 @@ constexpr int kTwStride = 68;             // 32 float2 + pad
 constexpr int kWinStride = 36;            // 32 floats + pad
 constexpr int kXStride = 34;              // exchange buffer row stride in float2 (even: 128-bit reads)
 constexpr int kItemRow = 544;             // item form: float2 per pair-row in natural bin order (513 bins + room to read a class length past the end)
+constexpr int kItemRegion = 4 * 2 * kItemRow;   // item form: floats per warp, a whole number of 128-byte lines (a stride of 187.5 lines was measured 12 % slower:
+                                                // every other warp's 256-byte accesses then straddle three lines)
+static_assert(kItemRegion % 32 == 0, "warp regions start on 128-byte lines");
 constexpr int kWabStride = 36;            // floats per lane in the (a, b) weight table: 17 float2 + pad, 36*l mod 32 = 4l
 // Two real channels share each complex transform; splitting the packed spectrum leaves a channel with its partner's
 // rounding noise, about -120 dB relative to the PARTNER (measured: tests/test_imbalance_gpu.py).  A frame in which some
@@ -104,7 +107,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride          (item form: iw, iP * 32 float2)
     int* gseg_s = reinterpret_cast<int*>(wab_s + (kItem ? 64 * pd.iP : 32 * kWabStride));   // gseg_pad (item form: none)
     float* R_all = reinterpret_cast<float*>(gseg_s + (kItem ? 0 : pd.gseg_pad));            // W * region
-    constexpr int region = kItem ? 4 * 2 * kItemRow : kRegion;             // floats per warp (the exchange buffer aliases it)
+    constexpr int region = kItem ? kItemRegion : kRegion;                  // floats per warp (the exchange buffer aliases it)
     int* marked_s = reinterpret_cast<int*>(R_all + W * region);            // main form: some warp of this block marked a frame
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -633,7 +636,8 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                         q[0 * kPS] = p02;
                         q[1 * kPS] = p13;
                         q[2 * kPS] = vmuls(i13, inv);
-                        q[3 * kPS] = make_float2(i2 * inv, 0.0f);
+                        if constexpr (kItem) R[3 * 2 * kItemRow + 32 * kb + lane] = i2 * inv;   // the seventh row has no partner: plain floats
+                        else q[3 * kPS] = make_float2(i2 * inv, 0.0f);
                     }
                 } else {
                     if (kb < 16 || lane == 0) {
@@ -658,16 +662,18 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 a3[c] = make_float2(0.0f, 0.0f);
                 const int Lc = pd.iL[c];
                 const float2* qp = Q + ist[c];
+                const float* q3p = R + 3 * 2 * kItemRow + ist[c];
                 const float2* wp = iw_s + 32 * pd.ioff[c] + lane;
 #pragma unroll 4
-                for (int j = 0; j < Lc; ++j, ++qp, wp += 32) {
-                    const float2 q0 = qp[0], q1 = qp[kItemRow], q2 = qp[2 * kItemRow], q3 = qp[3 * kItemRow];
+                for (int j = 0; j < Lc; ++j, ++qp, ++q3p, wp += 32) {
+                    const float2 q0 = qp[0], q1 = qp[kItemRow], q2 = qp[2 * kItemRow];
+                    const float q3 = *q3p;
                     const float2 w = *wp;
                     const float2 aa = make_float2(w.x, w.x), bb = make_float2(w.y, w.y);
                     aU[c][0] = __ffma2_rn(aa, q0, aU[c][0]); aV[c][0] = __ffma2_rn(bb, q0, aV[c][0]);
                     aU[c][1] = __ffma2_rn(aa, q1, aU[c][1]); aV[c][1] = __ffma2_rn(bb, q1, aV[c][1]);
                     aU[c][2] = __ffma2_rn(aa, q2, aU[c][2]); aV[c][2] = __ffma2_rn(bb, q2, aV[c][2]);
-                    a3[c] = __ffma2_rn(w, make_float2(q3.x, q3.x), a3[c]);
+                    a3[c] = __ffma2_rn(w, make_float2(q3, q3), a3[c]);
                 }
             });
             __syncwarp();                                                   // every lane is through with the rows: the sums may overwrite them
@@ -884,7 +890,7 @@ bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin) {
 int foa_iv2_frames_per_tile() { return iv2_warps(); }
 
 static size_t iv2_item_smem_bytes(const PlanDev& pd, int W) {
-    return (size_t)(32 * kTwStride + 32 * kWinStride + 64 * pd.iP + W * 4 * 2 * kItemRow + 4) * sizeof(float);
+    return (size_t)(32 * kTwStride + 32 * kWinStride + 64 * pd.iP + W * kItemRegion + 4) * sizeof(float);
 }
 
 template <int W, typename TIn, bool kIV, bool kItem = false>
@@ -921,6 +927,10 @@ extern "C" void seld_dev_phase_cycles(unsigned long long* out, int reset) {
 
 cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
 #ifdef SELD_IV2_W
+    if (pd.item_ok && iv2_item_smem_bytes(pd, SELD_IV2_W) <= 227 * 1024) {
+        if (a.in_i16) return iv2_launch_t<SELD_IV2_W, int16_t, true, true>(a, pd, sm_count, st);
+        return iv2_launch_t<SELD_IV2_W, float, true, true>(a, pd, sm_count, st);
+    }
     if (a.in_i16) return iv2_launch_t<SELD_IV2_W, int16_t, true>(a, pd, sm_count, st);
     return iv2_launch_t<SELD_IV2_W, float, true>(a, pd, sm_count, st);
 #endif
