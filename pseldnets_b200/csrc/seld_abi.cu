@@ -38,7 +38,12 @@ struct seld_plan {
     bool iv2_ok;           // the fp32 mel-walk kernel can take this bank (fallback of iv5 for unaligned outputs)
     bool lm4_ok;           // log-mel-only mode of the iv2 kernel available (channels beyond the first four, Logmel_Extractor)
     void* blob;            // one device allocation holding every table
+    int* redo_pool;        // kRedoPairs pairs of ints (inside the blob), zero between launches: see FoaArgs::redo_flags
+    mutable unsigned redo_next;
 };
+constexpr unsigned kRedoPairs = 256;
+// every launch that may mark frames gets its own pair, so launches of one plan on different streams do not share state
+static int* next_redo_flags(const seld_plan* p) { return p->redo_pool + 2 * (__atomic_fetch_add(&p->redo_next, 1u, __ATOMIC_RELAXED) % kRedoPairs); }
 
 static std::atomic<uint64_t> g_launches{0};
 static thread_local int g_last_cuda = 0;
@@ -190,12 +195,12 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                     }
                     if (!ok || (int)pc.size() > 32 * K || pc.empty()) continue;
                     std::stable_sort(pc.begin(), pc.end(), [](const Piece& x, const Piece& y) { return x.n > y.n; });
-                    for (int slack = 0; slack <= 2; ++slack) {
+                    for (int slack = 0; slack <= 4; slack += 4) {
                         long cost = 28L * K; int P = 0;
                         for (int c = 0; c < K; ++c) {
                             if ((size_t)(32 * c) >= pc.size()) continue;
                             std::vector<Piece> cl(pc.begin() + 32 * c, pc.begin() + std::min(pc.size(), (size_t)32 * (c + 1)));
-                            const int L = cl[0].n + slack;
+                            const int L = (cl[0].n + slack + 3) & ~3;   // the kernel walks a class four positions at a time
                             const Place pl = place_class(cl, L);
                             cost += (long)L * (7 * pl.wf + 12) / 2;    // per position: 3.5 loads of pl.wf wavefronts, the weights, the arithmetic
                             P += L;
@@ -206,7 +211,7 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                 }
             if (bestCost >= 0) {
                 iK = bestK;
-                for (int c = 0; c < 4; ++c) { iL[c] = (c < iK && (size_t)(32 * c) < best.size()) ? best[32 * c].n + bestSlack : 0; }
+                for (int c = 0; c < 4; ++c) { iL[c] = (c < iK && (size_t)(32 * c) < best.size()) ? (best[32 * c].n + bestSlack + 3) & ~3 : 0; }
                 for (int c = 0; c < 4; ++c) { ioff[c] = iP; iP += iL[c]; }
                 if (iP >= 8 && iP <= 24) {
                     item_ok = 1;
@@ -319,7 +324,7 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     const size_t b_wab = wab.size() * 4, b_rm = 32 * 4, b_g0 = 32 * 4, b_gs = (size_t)gseg_pad * 4;
     const size_t b_tw4 = tw4.size() * 4, b_win2 = win2.size() * 4, b_bimg = bimg.size() * 2;
     const size_t b_iw = iw.size() * 4, b_idst = istart.size() * 4, b_islot = islot.size() * 4;
-    const size_t total = b_tw + b_win + b_wt + 3 * b_i + b_wab + b_rm + b_g0 + b_gs + b_tw4 + b_win2 + b_bimg + 16 + b_iw + b_idst + b_islot + 32;
+    const size_t total = b_tw + b_win + b_wt + 3 * b_i + b_wab + b_rm + b_g0 + b_gs + b_tw4 + b_win2 + b_bimg + 16 + b_iw + b_idst + b_islot + 32 + 16 + 2 * kRedoPairs * 4;
     e = cudaMalloc(&p->blob, total);
     if (e != cudaSuccess) { cudaSetDevice(prev); delete p; return cuda_fail(e); }
     std::vector<unsigned char> host(total, 0);
@@ -342,6 +347,8 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     memcpy(&host[o], iw.data(), b_iw); const size_t o_iw = o; o += b_iw;
     memcpy(&host[o], istart.data(), b_idst); const size_t o_idst = o; o += b_idst;
     memcpy(&host[o], islot.data(), b_islot); const size_t o_islot = o; o += b_islot;
+    o = (o + 15) & ~(size_t)15;
+    const size_t o_redo = o; o += 2 * kRedoPairs * 4;                  // zeros
     e = cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { cudaFree(p->blob); delete p; return cuda_fail(e); }
@@ -364,6 +371,7 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
     memcpy(p->mt.chunk, mt_chunk, sizeof(mt_chunk));
     p->dev.gseg_pad = gseg_pad;
     p->dev.fast_ok = fast_ok;
+    p->redo_pool = (int*)(d + o_redo); p->redo_next = 0;
     p->dev.iw = (const float2*)(d + o_iw);
     p->dev.istart = (const int*)(d + o_idst);
     p->dev.islot = (const uint32_t*)(d + o_islot);
@@ -464,7 +472,7 @@ static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C,
         else if (kern == 5) e = seld::foa_iv5_launch(a, p->dev, p->mt, p->sm_count, st);
         else if (kern == 3) e = seld::foa_iv3_launch(a, p->dev, p->sm_count, st);
 #endif
-        else e = seld::foa_iv2_launch(a, p->dev, p->sm_count, st);
+        else { a.redo_flags = next_redo_flags(p); e = seld::foa_iv2_launch(a, p->dev, p->sm_count, st); }
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (C == 4) return SELD_OK;
@@ -477,6 +485,7 @@ static int run_foa(const seld_plan* p, bool iv, const void* x, int64_t B, int C,
         const int64_t tpc = (jobs + jpt - 1) / jpt;
         if (B * tpc > INT32_MAX) return SELD_EUNSUPPORTED;
         a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc);
+        a.redo_flags = next_redo_flags(p);
         cudaError_t e = seld::foa_lm4_launch(a, p->dev, p->sm_count, st);
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -619,6 +628,7 @@ extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B
     a.B = (int)B; a.C = C; a.Cout = C + C * (C - 1) / 2; a.T = (int)T; a.c_lo = 0;
     a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.span = 0; a.vec_ok = 0; a.in_i16 = 0; a.in_scale = 1.0f;
     const bool use_top_db = top_db >= 0.0f;
+    a.redo_flags = next_redo_flags(p);
     cudaError_t e = seld::mic_launch(a, p->dev, (int*)workspace, top_db, use_top_db, p->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(use_top_db ? 2 : 1, std::memory_order_relaxed);
@@ -667,6 +677,7 @@ extern "C" int seld_logmel_gcc_from_spectra_f32(const seld_plan* p, const float*
     a.B = (int)B; a.C = C; a.Cout = C + C * (C - 1) / 2; a.T = (int)T; a.c_lo = 0;
     a.tiles_per_clip = (int)tpc; a.n_tiles = (int)(B * tpc); a.in_scale = 1.0f;
     const bool use_top_db = top_db >= 0.0f;
+    a.redo_flags = next_redo_flags(p);
     cudaError_t e = seld::mic_launch(a, p->dev, (int*)workspace, top_db, use_top_db, p->sm_count, (cudaStream_t)stream, true);
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(use_top_db ? 2 : 1, std::memory_order_relaxed);

@@ -99,7 +99,7 @@ __device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.f
 template <int W, typename TIn, bool kIV, bool kRedo = false, bool kItem = false>
 __global__ void __launch_bounds__(W * 32, 1)
 foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
-    static_assert(!kItem || (kIV && !kRedo), "item form: main form of the IV kernel only");
+    static_assert(!kItem || !kRedo, "item form: main form only (the redo form keeps the run form of the mel step)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // lane-major tables read with 128-bit loads: row stride = 4 (mod 32) words -> conflict-free
     float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: (cos, -sin) of W1024^(lane*brev5(p)), p = 0..31
@@ -112,22 +112,22 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float in_scale = a.in_scale;
-    // redo form: the work items of main block `a.redo_block`: its tiles redo_block, + redo_grid, ..., W items each
+    // redo form: the work items of main block `(int)blockIdx.x`: its tiles redo_block, + redo_grid, ..., W items each
     // (kIV: frames; log-mel only: groups of four (frame, channel) jobs), item j = (tile number j / W, warp slot j % W)
     const int redo_Cj = a.C - a.c_lo;
     const int64_t redo_J = (int64_t)a.T * redo_Cj;                          // log-mel only: jobs per clip
 #ifdef SELD_CONTIG
-    const int redo_t0 = kRedo ? (int)(((int64_t)a.redo_block * a.n_tiles) / a.redo_grid) : 0;
-    const int redo_tiles = kRedo ? (int)(((int64_t)(a.redo_block + 1) * a.n_tiles) / a.redo_grid) - redo_t0 : 0;
+    const int redo_t0 = kRedo ? (int)(((int64_t)(int)blockIdx.x * a.n_tiles) / a.redo_grid) : 0;
+    const int redo_tiles = kRedo ? (int)(((int64_t)((int)blockIdx.x + 1) * a.n_tiles) / a.redo_grid) - redo_t0 : 0;
 #else
-    const int redo_tiles = (kRedo && a.n_tiles > a.redo_block) ? (a.n_tiles - 1 - a.redo_block) / a.redo_grid + 1 : 0;
+    const int redo_tiles = (kRedo && a.n_tiles > (int)blockIdx.x) ? (a.n_tiles - 1 - (int)blockIdx.x) / a.redo_grid + 1 : 0;
 #endif
     const int redo_items = redo_tiles * W;
     auto redo_item = [&](int j, int& b, int& grp) -> bool {                 // false: no such frame / group
 #ifdef SELD_CONTIG
         const int tile = redo_t0 + j / W;
 #else
-        const int tile = a.redo_block + (j / W) * a.redo_grid;
+        const int tile = (int)blockIdx.x + (j / W) * a.redo_grid;
 #endif
         b = tile / a.tiles_per_clip;
         grp = (tile - b * a.tiles_per_clip) * W + (j % W);
@@ -306,8 +306,10 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 }
             };
             // imbalance check (see kTauRow / kTauW): rows 0..3 are the powers of the four transform slots, partners (0,1), (2,3)
-            auto unbalanced = [](const float (&v)[NR], float t0, float t) {
-                return v[0] < t0 * v[1] || v[1] < t * v[0] || v[2] < t * v[3] || v[3] < t * v[2];
+            // (log-mel only: a slot without a job is exactly zero and leaks nothing into its partner)
+            const bool pair01 = kIV || (vk[0] && vk[1]), pair23 = kIV || (vk[2] && vk[3]);
+            auto unbalanced = [&](const float (&v)[NR], float t0, float t) {
+                return (pair01 && (v[0] < t0 * v[1] || v[1] < t * v[0])) || (pair23 && (v[2] < t * v[3] || v[3] < t * v[2]));
             };
             // some aligned group of eight bands (a byte of the ballot) with three or more bits set
             auto clustered = [](uint32_t m) {
@@ -334,17 +336,19 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                                 const int iv0 = pv & 0xff, iv1 = (pv >> 8) & 0xff, iv2 = (pv >> 16) & 0xff, iv3 = pv >> 24;
                                 const int iu0 = pu & 0xff, iu1 = (pu >> 8) & 0xff, iu2 = (pu >> 16) & 0xff, iu3 = pu >> 24;
 #pragma unroll
-                                for (int f = 0; f < 3; ++f) {
+                                for (int f = 0; f < (kIV ? 3 : 2); ++f) {
                                     const float2* su = S + (2 * f) * kItemSlots;
                                     const float2* sv = su + kItemSlots;
                                     const float2 v0 = sv[iv0], v1 = sv[iv1], v2 = sv[iv2], u0 = su[iu0], u1 = su[iu1], u2 = su[iu2];
                                     if constexpr (kFour) vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, sv[iv3])), vadd(vadd(u0, u1), vadd(u2, su[iu3])));
                                     else vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
                                 }
-                                const float2* s3 = S + 6 * kItemSlots;
-                                float t3 = ((s3[iv0].y + s3[iv1].y) + s3[iv2].y) + ((s3[iu0].x + s3[iu1].x) + s3[iu2].x);
-                                if constexpr (kFour) t3 += s3[iv3].y + s3[iu3].x;
-                                vv[3] = make_float2(t3, 0.0f);
+                                if constexpr (kIV) {
+                                    const float2* s3 = S + 6 * kItemSlots;
+                                    float t3 = ((s3[iv0].y + s3[iv1].y) + s3[iv2].y) + ((s3[iu0].x + s3[iu1].x) + s3[iu2].x);
+                                    if constexpr (kFour) t3 += s3[iv3].y + s3[iu3].x;
+                                    vv[NP - 1] = make_float2(t3, 0.0f);
+                                }
                             } else {
 #pragma unroll
                                 for (int f = 0; f < NP; ++f) {
@@ -586,6 +590,26 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 #endif
         PHASE_MARK(5);   // second 32-pt
 
+        if constexpr (kItem) {
+            // ---------------- item form, untangle in the walk: the packed spectra go to shared memory as they are, bin k <= 512
+            // to the P planes and bin 1024 - k to the M planes at index k (natural order: consecutive lanes, consecutive words)
+            float2* const Pre = reinterpret_cast<float2*>(R);
+            float2* const Pim = Pre + kItemRow;
+            float2* const Mre = Pre + 2 * kItemRow;
+            float2* const Mim = Pre + 3 * kItemRow;
+            static_for<0, 16>([&](auto kbi) {
+                constexpr int kb = decltype(kbi)::value;
+                Pre[32 * kb + lane] = re[brev5(kb)]; Pim[32 * kb + lane] = im[brev5(kb)];
+            });
+            static_for<16, 32>([&](auto kbi) {
+                constexpr int kb = decltype(kbi)::value;                    // bin 32 kb + lane = 1024 - m
+                Mre[1024 - 32 * kb - lane] = re[brev5(kb)]; Mim[1024 - 32 * kb - lane] = im[brev5(kb)];
+            });
+            if (lane == 0) {                                                // bins 0 and 512 are their own mirror
+                Mre[0] = re[brev5(0)]; Mim[0] = im[brev5(0)];
+                Pre[512] = re[brev5(16)]; Pim[512] = im[brev5(16)];
+            }
+        } else
         // ---------------- per-bin quantities -> 7 rows
         {
             const int src = (32 - lane) & 31;
@@ -631,13 +655,11 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
 #else
                     if (kb < 16 || lane == 0) {
 #endif
-                        constexpr int kPS = kItem ? kItemRow : kPairWords / 2;            // float2 per pair-row
-                        float2* q = kItem ? reinterpret_cast<float2*>(R) + 32 * kb + lane : reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
-                        q[0 * kPS] = p02;
-                        q[1 * kPS] = p13;
-                        q[2 * kPS] = vmuls(i13, inv);
-                        if constexpr (kItem) R[3 * 2 * kItemRow + 32 * kb + lane] = i2 * inv;   // the seventh row has no partner: plain floats
-                        else q[3 * kPS] = make_float2(i2 * inv, 0.0f);
+                        float2* q = reinterpret_cast<float2*>(R + 64 * kb + wofs[kb & 3]);
+                        q[0 * (kPairWords / 2)] = p02;
+                        q[1 * (kPairWords / 2)] = p13;
+                        q[2 * (kPairWords / 2)] = vmuls(i13, inv);
+                        q[3 * (kPairWords / 2)] = make_float2(i2 * inv, 0.0f);
                     }
                 } else {
                     if (kb < 16 || lane == 0) {
@@ -661,19 +683,32 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 for (int f = 0; f < 3; ++f) { aU[c][f] = make_float2(0.0f, 0.0f); aV[c][f] = make_float2(0.0f, 0.0f); }
                 a3[c] = make_float2(0.0f, 0.0f);
                 const int Lc = pd.iL[c];
-                const float2* qp = Q + ist[c];
-                const float* q3p = R + 3 * 2 * kItemRow + ist[c];
+                const float2* zp = Q + ist[c];
                 const float2* wp = iw_s + 32 * pd.ioff[c] + lane;
-#pragma unroll 4
-                for (int j = 0; j < Lc; ++j, ++qp, ++q3p, wp += 32) {
-                    const float2 q0 = qp[0], q1 = qp[kItemRow], q2 = qp[2 * kItemRow];
-                    const float q3 = *q3p;
+#pragma unroll 1
+                for (int j0 = 0; j0 < Lc; j0 += 4)                          // class lengths are multiples of four: no remainder code
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj, ++zp, wp += 32) {
+                    const float2 zr = zp[0], zi = zp[kItemRow], pr = zp[2 * kItemRow], pi = zp[3 * kItemRow];
                     const float2 w = *wp;
+                    // window was pre-scaled by 0.5: A = Z[k] + conj(Z[N-k]), B = (Z[k] - conj(Z[N-k])) / i
+                    const float2 ar = vadd(zr, pr), ai = vsub(zi, pi);      // (X0, X2)
+                    const float2 br = vadd(zi, pi), bi = vsub(pr, zr);      // (X1, X3)
+                    const float2 p02 = __ffma2_rn(ai, ai, __fmul2_rn(ar, ar));
+                    const float2 p13 = __ffma2_rn(bi, bi, __fmul2_rn(br, br));
                     const float2 aa = make_float2(w.x, w.x), bb = make_float2(w.y, w.y);
-                    aU[c][0] = __ffma2_rn(aa, q0, aU[c][0]); aV[c][0] = __ffma2_rn(bb, q0, aV[c][0]);
-                    aU[c][1] = __ffma2_rn(aa, q1, aU[c][1]); aV[c][1] = __ffma2_rn(bb, q1, aV[c][1]);
-                    aU[c][2] = __ffma2_rn(aa, q2, aU[c][2]); aV[c][2] = __ffma2_rn(bb, q2, aV[c][2]);
-                    a3[c] = __ffma2_rn(w, make_float2(q3, q3), a3[c]);
+                    aU[c][0] = __ffma2_rn(aa, p02, aU[c][0]); aV[c][0] = __ffma2_rn(bb, p02, aV[c][0]);
+                    aU[c][1] = __ffma2_rn(aa, p13, aU[c][1]); aV[c][1] = __ffma2_rn(bb, p13, aV[c][1]);
+                    if constexpr (kIV) {
+                        const float2 i13 = vfmas(bi, ai.x, vmuls(br, ar.x));    // Re(conj(X0) X1), Re(conj(X0) X3)
+                        const float i2 = fmaf(ai.x, ai.y, ar.x * ar.y);         // Re(conj(X0) X2)
+                        const float sq = fmaf(i13.y, i13.y, fmaf(i2, i2, i13.x * i13.x));
+                        const float inv = rcp_ftz(sqrt_ftz(sq) + eps);          // one MUFU each; sqrt(0) = 0, subnormal sums flush to 0 (far below eps)
+                        const float2 n13 = vmuls(i13, inv);
+                        const float n2 = i2 * inv;
+                        aU[c][2] = __ffma2_rn(aa, n13, aU[c][2]); aV[c][2] = __ffma2_rn(bb, n13, aV[c][2]);
+                        a3[c] = __ffma2_rn(w, make_float2(n2, n2), a3[c]);
+                    }
                 }
             });
             __syncwarp();                                                   // every lane is through with the rows: the sums may overwrite them
@@ -683,14 +718,14 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 constexpr int c = decltype(ci)::value;
                 if (c < pd.iK) {
 #pragma unroll
-                    for (int f = 0; f < 3; ++f) {
+                    for (int f = 0; f < (kIV ? 3 : 2); ++f) {
                         S[(2 * f) * kItemSlots + 32 * c + lane] = aU[c][f];
                         S[(2 * f + 1) * kItemSlots + 32 * c + lane] = aV[c][f];
                     }
-                    S[6 * kItemSlots + 32 * c + lane] = a3[c];
+                    if constexpr (kIV) S[6 * kItemSlots + 32 * c + lane] = a3[c];
                 }
             });
-            if (lane < 7) S[lane * kItemSlots + kItemZero] = make_float2(0.0f, 0.0f);
+            if (lane < (kIV ? 7 : 4)) S[lane * kItemSlots + kItemZero] = make_float2(0.0f, 0.0f);
             __syncwarp();
         }
 
@@ -710,10 +745,21 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         PHASE_MARK(8);   // mel combine + store
     }
     __syncthreads();
-    if (tid == 0 && *marked_s != 0) {
-        FoaArgs ar = a;
-        ar.redo_block = (int)blockIdx.x; ar.redo_grid = (int)gridDim.x;
-        foa_iv2_kernel<W, TIn, kIV, true><<<1, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd);
+    if (tid == 0) {
+        // the last block to finish launches the redo grid if any block marked a frame (one launch, all SMs; tail launches of
+        // single blocks would run one after the other)
+        if (*marked_s != 0) atomicExch(&a.redo_flags[1], 1);
+        __threadfence();
+        if (atomicAdd(&a.redo_flags[0], 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            const int any = atomicExch(&a.redo_flags[1], 0);
+            atomicExch(&a.redo_flags[0], 0);                               // ready for the next launch that is handed this pair
+            if (any) {
+                FoaArgs ar = a;
+                ar.redo_grid = (int)gridDim.x;
+                foa_iv2_kernel<W, TIn, kIV, true><<<gridDim.x, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd);
+            }
+        }
     }
 
     } else {
@@ -951,6 +997,9 @@ cudaError_t foa_iv2_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cu
 // 8 warps x 4 (frame, channel) jobs
 int foa_lm4_jobs_per_tile() { return 8 * 4; }
 cudaError_t foa_lm4_launch(const FoaArgs& a, const PlanDev& pd, int sm_count, cudaStream_t st) {
+#ifndef SELD_NO_ITEM
+    if (pd.item_ok && iv2_item_smem_bytes(pd, 8) <= 227 * 1024) return iv2_launch_t<8, float, false, true>(a, pd, sm_count, st);
+#endif
     return iv2_launch_t<8, float, false>(a, pd, sm_count, st);
 }
 

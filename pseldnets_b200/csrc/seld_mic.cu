@@ -141,12 +141,12 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     // frames of this warp: the main form walks its tiles; the redo form looks at 32 frames at a time (one per lane)
     // and then takes the marked ones in turn
     int tile = blockIdx.x - gridDim.x;
-    // redo form (one block, launched from the device by block a.redo_block of a main grid of a.redo_grid blocks): item j
+    // redo form (one block, launched from the device by block (int)blockIdx.x of a main grid of a.redo_grid blocks): item j
     // = (tile number j / W of that block, warp slot j % W)
-    const int redo_tiles = (kRedo && a.n_tiles > a.redo_block) ? (a.n_tiles - 1 - a.redo_block) / a.redo_grid + 1 : 0;
+    const int redo_tiles = (kRedo && a.n_tiles > (int)blockIdx.x) ? (a.n_tiles - 1 - (int)blockIdx.x) / a.redo_grid + 1 : 0;
     const int redo_items = redo_tiles * W;
     auto redo_item = [&](int j, int& b, int& t) -> bool {
-        const int tl = a.redo_block + (j / W) * a.redo_grid;
+        const int tl = (int)blockIdx.x + (j / W) * a.redo_grid;
         b = tl / a.tiles_per_clip;
         t = (tl - b * a.tiles_per_clip) * W + (j % W);
         return j < redo_items && t < a.T;
@@ -559,10 +559,19 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         // a block that marked frames launches the redo form for them into the tail of this grid: it runs when the whole
         // grid is done and before the stream's next kernel (the top_db floor)
         __syncthreads();
-        if (tid == 0 && *marked_s != 0) {
-            FoaArgs ar = a;
-            ar.redo_block = (int)blockIdx.x; ar.redo_grid = (int)gridDim.x;
-            mic_features_kernel<0, true><<<1, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd, maxkey);
+        if (tid == 0) {                                                     // the last block to finish launches one redo grid (as in seld_foa_iv2.cu)
+            if (*marked_s != 0) atomicExch(&a.redo_flags[1], 1);
+            __threadfence();
+            if (atomicAdd(&a.redo_flags[0], 1) == (int)gridDim.x - 1) {
+                __threadfence();
+                const int any = atomicExch(&a.redo_flags[1], 0);
+                atomicExch(&a.redo_flags[0], 0);
+                if (any) {
+                    FoaArgs ar = a;
+                    ar.redo_grid = (int)gridDim.x;
+                    mic_features_kernel<0, true><<<gridDim.x, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd, maxkey);
+                }
+            }
         }
     }
 }

@@ -62,7 +62,8 @@ struct FoaArgs {
     int c_lo;                // first input channel this launch covers (log-mel of channels c_lo..C-1)
     int tiles_per_clip, n_tiles;
     int step_clip, step_tile;  // iv2: grid size split as step_clip * tiles_per_clip + step_tile (set by the launcher)
-    int redo_block, redo_grid; // redo form (launched from the device by block `redo_block` of a main grid of `redo_grid` blocks)
+    int redo_grid;             // redo form: blocks of the main grid (redo block i looks through the frames main block i processed)
+    int* redo_flags;           // [0] blocks of the main grid that have finished, [1] some block marked a frame; both zero between launches
     int smem_bytes;            // dynamic shared memory of the launch (the device-side launch of the redo form needs it)
     void* spec;              // MIC only: (B, T, 513, 4) complex64 spectrogram, written (spectrogram mode) or read (from-spectra mode)
     int span;                // staged samples per channel per tile (multiple of 4)
