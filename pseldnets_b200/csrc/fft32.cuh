@@ -118,14 +118,83 @@ __device__ __forceinline__ void dif_stage(V (&re)[32], V (&im)[32]) {
     });
 }
 
+// ---- decimation in time with natural-order input and bit-reversed output: the twiddle of a butterfly depends on its
+// group only, and multiplies the second input BEFORE the add/subtract.  That form fuses: with w = c (1 - i t), t = tan,
+//   b w = c (br + t bi, bi - t br),   a +- b w = a +- c * tmp
+// is 2 + 4 fused multiply-adds per butterfly instead of 4 adds + 4 multiplies (cotangent form where |c| < |s|); the
+// (1 -+ i) / sqrt2 twiddles take 2 adds + 4 FMAs instead of 6 adds + 2 multiplies.  68 fewer operations per 32-point
+// transform than the decimation-in-frequency form above (388 instead of 456), one rounding less per output.
+__host__ __device__ constexpr int brev_n(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+__host__ __device__ constexpr int ilog2(int x) { int r = 0; while (x > 1) { x >>= 1; ++r; } return r; }
+
+// (ar, ai), (br, bi) -> a + b W32^K, a - b W32^K        K in [0, 16)
+template <int K, class V>
+__device__ __forceinline__ void dit_bfly(V& ar, V& ai, V& br, V& bi) {
+    if constexpr (K == 0) {
+        const V r0 = vadd(ar, br), i0 = vadd(ai, bi), r1 = vsub(ar, br), i1 = vsub(ai, bi);
+        ar = r0; ai = i0; br = r1; bi = i1;
+    } else if constexpr (K == 8) {                 // b * (-i) = (bi, -br)
+        const V r0 = vadd(ar, bi), i0 = vsub(ai, br), r1 = vsub(ar, bi), i1 = vadd(ai, br);
+        ar = r0; ai = i0; br = r1; bi = i1;
+    } else if constexpr (K == 4) {                 // b * h (1 - i) = h (br + bi, bi - br)
+        constexpr float h = (float)cos32(4);
+        const V tr = vadd(br, bi), ti = vsub(bi, br);
+        const V r0 = vfmas(tr, h, ar), i0 = vfmas(ti, h, ai), r1 = vfmas(tr, -h, ar), i1 = vfmas(ti, -h, ai);
+        ar = r0; ai = i0; br = r1; bi = i1;
+    } else if constexpr (K == 12) {                // b * (-h) (1 + i) = -h (br - bi, br + bi)
+        constexpr float h = (float)cos32(4);
+        const V tr = vsub(br, bi), ti = vadd(br, bi);
+        const V r0 = vfmas(tr, -h, ar), i0 = vfmas(ti, -h, ai), r1 = vfmas(tr, h, ar), i1 = vfmas(ti, h, ai);
+        ar = r0; ai = i0; br = r1; bi = i1;
+    } else {
+        // W32^K = c - i s:  b w = (br c + bi s, bi c - br s)
+        constexpr double cd = cos32(K), sd = sin32(K);
+        if constexpr ((cd < 0 ? -cd : cd) >= sd) {  // = c (br + t bi, bi - t br)
+            constexpr float t = (float)(sd / cd), c = (float)cd;
+            const V tr = vfmas(bi, t, br), ti = vfmas(br, -t, bi);
+            const V r0 = vfmas(tr, c, ar), i0 = vfmas(ti, c, ai), r1 = vfmas(tr, -c, ar), i1 = vfmas(ti, -c, ai);
+            ar = r0; ai = i0; br = r1; bi = i1;
+        } else {                                   // = s (u br + bi, u bi - br),  u = c / s
+            constexpr float u = (float)(cd / sd), sn = (float)sd;
+            const V tr = vfmas(br, u, bi), ti = vfmas(bi, u, vneg(br));
+            const V r0 = vfmas(tr, sn, ar), i0 = vfmas(ti, sn, ai), r1 = vfmas(tr, -sn, ar), i1 = vfmas(ti, -sn, ai);
+            ar = r0; ai = i0; br = r1; bi = i1;
+        }
+    }
+}
+
+// One DIT stage: butterflies of span HALF inside groups of 2*HALF; group g uses W32^(HALF * brev(g)).
+template <int HALF, class V>
+__device__ __forceinline__ void dit_stage(V (&re)[32], V (&im)[32]) {
+    static_for<0, 16>([&](auto bi_) {
+        constexpr int b = decltype(bi_)::value;
+        constexpr int g = b / HALF, k = b % HALF;
+        constexpr int i0 = g * 2 * HALF + k, i1 = i0 + HALF;
+        constexpr int K = HALF * brev_n(g, ilog2(16 / HALF));
+        dit_bfly<K>(re[i0], im[i0], re[i1], im[i1]);
+    });
+}
+
 // In-place forward 32-point DFT; result X[brev5(p)] at position p.
 template <class V>
 __device__ __forceinline__ void fft32(V (&re)[32], V (&im)[32]) {
+#ifdef SELD_FFT_DIF
     dif_stage<16>(re, im);
     dif_stage<8>(re, im);
     dif_stage<4>(re, im);
     dif_stage<2>(re, im);
     dif_stage<1>(re, im);
+#else
+    dit_stage<16>(re, im);
+    dit_stage<8>(re, im);
+    dit_stage<4>(re, im);
+    dit_stage<2>(re, im);
+    dit_stage<1>(re, im);
+#endif
 }
 
 

@@ -33,14 +33,18 @@ namespace mic {
 using namespace melseg;
 
 constexpr int kW = 8;                      // warps (frames) per block
-constexpr int kSpecStride = 516;           // float2 per channel spectrum (513 + pad)
+constexpr int kSpecStride = 528;           // float2 per channel spectrum: 513 + pad to a whole number of 128-byte lines (with 516 the
+                                           // 256-byte warp accesses of channels 1-3 straddled three lines instead of two)
 constexpr int kSpec = 4 * kSpecStride * 2; // floats: four spectra
 constexpr int kXStride = 34;                // exchange buffer row stride in float2 (even: 128-bit reads)
 constexpr int kRowsArea = 32 * kXStride * 2; // floats: 32x34 float2 exchange buffer; the 4 power rows (2112) alias it
 constexpr int kTwStride = 68;               // lane-major twiddle table row: 32 float2 + pad
 constexpr int kWinStride = 36;              // lane-major window table row: 32 floats + pad
-constexpr int kZeroRun = 127;               // float2 slot of every row kept at (0, 0) during the combine step
+constexpr int kItemRow = 544;               // float2 per power pair-row in natural bin order: (P0, P2) and (P1, P3) fill the exchange area exactly
+constexpr int kItemSlots = 136, kItemZero = 128;   // piece sums: 4 arrays of kItemSlots float2 (4 classes x 32 lanes, the slot kept at zero, pad)
+static_assert(2 * 2 * kItemRow <= kRowsArea && 4 * 2 * kItemSlots <= kRowsArea, "rows and piece sums live in the exchange area");
 constexpr int kRegion = kSpec + kRowsArea;
+static_assert(kRegion % 32 == 0 && kSpec % 32 == 0 && (kSpecStride * 2) % 32 == 0, "per-warp regions and their parts start on 128-byte lines");
 // imbalance rule as in seld_foa_iv2.cu: a loose ratio that three of eight neighbouring bands must cross, a strict one
 // that a single band may cross; every microphone's phases enter three GCC planes, hence the loose ratio of 40 dB
 constexpr float kTauLoose = 1e-4f, kTauStrict = 1e-7f;
@@ -84,9 +88,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     // lane-major tables read with 128-bit loads (row stride = 4 mod 32 words: conflict-free)
     float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: W1024^(lane*brev5(p)) as (cos_p, cos_p+1, -sin_p, -sin_p+1), p even
     float* win_s = tw_s + 32 * kTwStride;                                  // [lane][kWinStride]: window[32*m + lane] * 0.5
-    float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride
-    int* gseg_s = reinterpret_cast<int*>(wab_s + 32 * kWabStride);         // gseg_pad
-    float* R_all = reinterpret_cast<float*>(gseg_s + pd.gseg_pad);         // W * kRegion
+    float* wab_s = win_s + 32 * kWinStride;                                // item form of the mel bank: iw, iP * 32 float2 (a, b)
+    float* R_all = wab_s + 64 * pd.iP;                                     // W * kRegion
     int* marked_s = reinterpret_cast<int*>(R_all + W * kRegion);           // main form: some warp of this block marked a frame
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -96,33 +99,26 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         tw_s[l * kTwStride + 4 * (r >> 1) + (r & 1)] = w.x; tw_s[l * kTwStride + 4 * (r >> 1) + 2 + (r & 1)] = w.y;
         win_s[l * kWinStride + r] = pd.win[i];
     }
-    for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
-    for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
+    for (int i = tid; i < 64 * pd.iP; i += W * 32) wab_s[i] = reinterpret_cast<const float*>(pd.iw)[i];
     if (tid == 0) *marked_s = 0;
     __syncthreads();
 
     float2* spec = reinterpret_cast<float2*>(R_all + warp * kRegion);      // [4][kSpecStride]
     float* R = R_all + warp * kRegion + kSpec;                             // 4 rows / exchange buffer
     float2* scratch = reinterpret_cast<float2*>(R);
-    const uint32_t runmask = pd.runmask[lane];
-    const int g0 = pd.g0[lane];
     const int hop = pd.hop, M = pd.n_mels;
     const float amin = pd.amin;
-    int wofs[4], rofs[4];
-    lane_offsets(lane, wofs, rofs);
     const int64_t ch_stride = (int64_t)a.T * M;
     const int src = (32 - lane) & 31;
-
-    auto pack_runs = [&](int lo, int hi) {
-        uint32_t p = 0;
+    // mel step in its item form (see seld_foa_iv2.cu): lane l walks one piece of a segment per class, from bin ist[c] on;
+    // bands lane and lane + 32 then add up at most four piece sums per list (segment m: V sums, segment m + 1: U sums)
+    int ist[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) p |= (uint32_t)(lo + i < hi ? lo + i : kZeroRun) << (8 * i);
-        return p;
-    };
-    const uint32_t slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]), slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]);
-    const uint32_t slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]), slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]);
-    const bool four = __any_sync(0xffffffffu, (slotV0 >> 24) != kZeroRun || (slotU0 >> 24) != kZeroRun ||
-                                              (slotV1 >> 24) != kZeroRun || (slotU1 >> 24) != kZeroRun);
+    for (int c = 0; c < 4; ++c) ist[c] = pd.istart[c * 32 + lane];
+    const uint32_t slotV0 = pd.islot[2 * lane], slotU0 = pd.islot[2 * lane + 1];
+    const uint32_t slotV1 = pd.islot[2 * (lane + 32)], slotU1 = pd.islot[2 * (lane + 32) + 1];
+    const bool four = __any_sync(0xffffffffu, (slotV0 >> 24) != kItemZero || (slotU0 >> 24) != kItemZero ||
+                                              (slotV1 >> 24) != kItemZero || (slotU1 >> 24) != kItemZero);
 
     int cur_b = -1;
     float rmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -140,13 +136,16 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
 
     // frames of this warp: the main form walks its tiles; the redo form looks at 32 frames at a time (one per lane)
     // and then takes the marked ones in turn
-    int tile = blockIdx.x - gridDim.x;
-    // redo form (one block, launched from the device by block (int)blockIdx.x of a main grid of a.redo_grid blocks): item j
-    // = (tile number j / W of that block, warp slot j % W)
-    const int redo_tiles = (kRedo && a.n_tiles > (int)blockIdx.x) ? (a.n_tiles - 1 - (int)blockIdx.x) / a.redo_grid + 1 : 0;
+    // a block owns a contiguous range of tiles (neighbouring tiles share samples in L1; -3 % against grid-stride tiles in
+    // the FOA kernel, -2 % here); block i of the redo grid looks through the tiles of main block i
+    const int nblk = kRedo ? a.redo_grid : (int)gridDim.x;
+    const int tile_lo = (int)(((int64_t)blockIdx.x * a.n_tiles) / nblk), tile_hi = (int)(((int64_t)(blockIdx.x + 1) * a.n_tiles) / nblk);
+    int tile = tile_lo - 1;
+    // redo form: item j = (tile number j / W of that block, warp slot j % W)
+    const int redo_tiles = kRedo ? tile_hi - tile_lo : 0;
     const int redo_items = redo_tiles * W;
     auto redo_item = [&](int j, int& b, int& t) -> bool {
-        const int tl = (int)blockIdx.x + (j / W) * a.redo_grid;
+        const int tl = tile_lo + j / W;
         b = tl / a.tiles_per_clip;
         t = (tl - b * a.tiles_per_clip) * W + (j % W);
         return j < redo_items && t < a.T;
@@ -156,8 +155,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     for (;;) {
         int b, t;
         if constexpr (!kRedo) {
-            tile += gridDim.x;
-            if (tile >= a.n_tiles) break;
+            ++tile;
+            if (tile >= tile_hi) break;
             b = tile / a.tiles_per_clip;
             t = (tile - b * a.tiles_per_clip) * W + warp;
             if (t >= a.T) continue;
@@ -310,12 +309,9 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     const float2 ur = __fmul2_rn(ar, n02), ui = __fmul2_rn(ai, n02);
                     spec[pass * kSpecStride + k] = make_float2(ur.x, ui.x);
                     spec[(pass + 2) * kSpecStride + k] = make_float2(ur.y, ui.y);
-                    if (pass == 1) {
-                        float* q = R + 32 * kb + wofs[kb & 3];
-                        q[0 * kRowWords] = keep02[kb].x;
-                        q[1 * kRowWords] = p02.x;
-                        q[2 * kRowWords] = keep02[kb].y;
-                        q[3 * kRowWords] = p02.y;
+                    if (pass == 1) {                                        // pair rows (P0, P2), (P1, P3) in natural bin order
+                        reinterpret_cast<float2*>(R)[k] = keep02[kb];
+                        reinterpret_cast<float2*>(R)[kItemRow + k] = p02;
                     }
                 }
                 if (pass == 0) keep02[kb] = p02;
@@ -332,11 +328,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 spec[1 * kSpecStride + k] = make_float2(ur13.x, ui13.x);
                 spec[2 * kSpecStride + k] = make_float2(ur02.y, ui02.y);
                 spec[3 * kSpecStride + k] = make_float2(ur13.y, ui13.y);
-                float* q = R + 32 * kb + wofs[kb & 3];
-                q[0 * kRowWords] = p02.x;
-                q[1 * kRowWords] = p13.x;
-                q[2 * kRowWords] = p02.y;
-                q[3 * kRowWords] = p13.y;
+                reinterpret_cast<float2*>(R)[k] = p02;                      // pair rows (P0, P2), (P1, P3) in natural bin order
+                reinterpret_cast<float2*>(R)[kItemRow + k] = p13;
             }
         });
         __syncwarp();
@@ -345,11 +338,41 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
 
         // ---------------- log-mel of the four power rows (unclamped dB + running maximum)
         float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
+#ifndef MABL_NOMEL
         {
-            float2 wv[17];
-            load_weights(wab_s, lane, wv);
-            mel_walk<4, 0, 1, 2, 3>(R, wv, rofs, runmask, g0, lane);
-            if (lane < 4) reinterpret_cast<float2*>(R + lane * kRowWords)[kZeroRun] = make_float2(0.f, 0.f);   // bins long consumed
+            float2 aU[4][2], aV[4][2];                                      // piece sums per class, both pair rows
+            {
+                const float2* const iw_s = reinterpret_cast<const float2*>(wab_s);
+                const float2* const Q = reinterpret_cast<const float2*>(R);
+                static_for<0, 4>([&](auto ci) {
+                    constexpr int c = decltype(ci)::value;
+                    aU[c][0] = aU[c][1] = aV[c][0] = aV[c][1] = make_float2(0.f, 0.f);
+                    const int Lc = pd.iL[c];
+                    const float2* qp = Q + ist[c];
+                    const float2* wp = iw_s + 32 * pd.ioff[c] + lane;
+#pragma unroll 1
+                    for (int j0 = 0; j0 < Lc; j0 += 4)                      // class lengths are multiples of four
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj, ++qp, wp += 32) {
+                        const float2 q0 = qp[0], q1 = qp[kItemRow], w = *wp;
+                        const float2 aa = make_float2(w.x, w.x), bb = make_float2(w.y, w.y);
+                        aU[c][0] = __ffma2_rn(aa, q0, aU[c][0]); aV[c][0] = __ffma2_rn(bb, q0, aV[c][0]);
+                        aU[c][1] = __ffma2_rn(aa, q1, aU[c][1]); aV[c][1] = __ffma2_rn(bb, q1, aV[c][1]);
+                    }
+                });
+            }
+            __syncwarp();                                                   // every lane is through with the rows: the sums may overwrite them
+            {
+                float2* const S = reinterpret_cast<float2*>(R);             // [U row 0 | V row 0 | U row 1 | V row 1], kItemSlots float2 each
+                static_for<0, 4>([&](auto ci) {
+                    constexpr int c = decltype(ci)::value;
+                    if (c < pd.iK) {
+                        S[0 * kItemSlots + 32 * c + lane] = aU[c][0]; S[1 * kItemSlots + 32 * c + lane] = aV[c][0];
+                        S[2 * kItemSlots + 32 * c + lane] = aU[c][1]; S[3 * kItemSlots + 32 * c + lane] = aV[c][1];
+                    }
+                });
+                if (lane < 4) S[lane * kItemSlots + kItemZero] = make_float2(0.f, 0.f);
+            }
             __syncwarp();
             // band per lane; run numbers of segment m (V) and m+1 (U) in fixed slots (absent -> the zero run), all
             // loads issued up front (n_mels == 64 on this path: bands lane and lane + 32)
@@ -373,19 +396,20 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     const int m = lane + 32 * r;
                     const uint32_t pv = r ? slotV1 : slotV0, pu = r ? slotU1 : slotU0;
                     float v[4];
+                    {
+                        const float2* S = reinterpret_cast<const float2*>(R);
+                        const int iv0 = pv & 0xff, iv1 = (pv >> 8) & 0xff, iv2 = (pv >> 16) & 0xff, iv3 = pv >> 24;
+                        const int iu0 = pu & 0xff, iu1 = (pu >> 8) & 0xff, iu2 = (pu >> 16) & 0xff, iu3 = pu >> 24;
+                        float2 vv[2];
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        const float* rowp = R + f * kRowWords;
-                        const float v0 = rowp[2 * (pv & 0xff) + 1], v1 = rowp[2 * ((pv >> 8) & 0xff) + 1];
-                        const float v2 = rowp[2 * ((pv >> 16) & 0xff) + 1];
-                        const float u0 = rowp[2 * (pu & 0xff)], u1 = rowp[2 * ((pu >> 8) & 0xff)];
-                        const float u2 = rowp[2 * ((pu >> 16) & 0xff)];
-                        if constexpr (kFour) {
-                            const float v3 = rowp[2 * (pv >> 24) + 1], u3 = rowp[2 * (pu >> 24)];
-                            v[f] = ((v0 + v1) + (v2 + v3)) + ((u0 + u1) + (u2 + u3));
-                        } else {
-                            v[f] = ((v0 + v1) + v2) + ((u0 + u1) + u2);
+                        for (int f = 0; f < 2; ++f) {
+                            const float2* su = S + (2 * f) * kItemSlots;
+                            const float2* sv = su + kItemSlots;
+                            const float2 v0 = sv[iv0], v1 = sv[iv1], v2 = sv[iv2], u0 = su[iu0], u1 = su[iu1], u2 = su[iu2];
+                            if constexpr (kFour) vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, sv[iv3])), vadd(vadd(u0, u1), vadd(u2, su[iu3])));
+                            else vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
                         }
+                        v[0] = vv[0].x; v[2] = vv[0].y; v[1] = vv[1].x; v[3] = vv[1].y;
                     }
                     if constexpr (kMode == 0 && !kRedo) {                   // every lane votes (no short-circuit in front of the ballot)
                         const uint32_t lm = __ballot_sync(0xffffffffu, unbalanced(v, kTauLoose));
@@ -411,6 +435,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 }
             }
         }
+#endif
 
         // ---------------- GCC-PHAT.  Two real correlations per complex inverse transform (Z = ph_a + i ph_b):
         // pass 0 = pairs (01, 02 | 03, 12) as two transforms packed in float2 halves, pass 1 = pairs (13, 23) as
@@ -425,6 +450,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         // angle(0) = 0: a vanishing cross-spectrum bin must contribute the phasor 1.  That needs two compares and a
         // select per product; frames without any vanishing bin (all but digital silence / dead channels) skip them.
         const bool any_zero = __any_sync(0xffffffffu, min_n == 0.0f);
+#ifndef MABL_NOGCC0
         {
             auto build = [&](auto check_c) {
                 constexpr bool kCheck = decltype(check_c)::value;
@@ -490,6 +516,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;
             g[3 * ch_stride + lane] = c31i.y * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.y * kInvN;
         }
+#endif
+#ifndef MABL_NOGCC1
         {
             // one transform: position p of (zr, zi) holds the input pair (z[m = 2p], z[m = 2p + 1])
             float2 zr[16], zi[16];
@@ -553,6 +581,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             g[0 * ch_stride + lane] = (a31r.x + a31r.y) * kInvN;  g[0 * ch_stride + 32 + lane] = (a0r.x + a0r.y) * kInvN;
             g[1 * ch_stride + lane] = (a31i.x + a31i.y) * kInvN;  g[1 * ch_stride + 32 + lane] = (a0i.x + a0i.y) * kInvN;
         }
+#endif
     }
     flush_max();
     if constexpr (kMode == 0 && !kRedo) {
@@ -595,11 +624,11 @@ __global__ void mic_topdb_kernel(float* __restrict__ out, const int* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 static size_t mic_smem_bytes(const PlanDev& pd) {
-    return (size_t)(32 * mic::kTwStride + 32 * mic::kWinStride + 32 * melseg::kWabStride + pd.gseg_pad + mic::kW * mic::kRegion + 4) * sizeof(float);
+    return (size_t)(32 * mic::kTwStride + 32 * mic::kWinStride + 64 * pd.iP + mic::kW * mic::kRegion + 4) * sizeof(float);
 }
 
 bool mic_supported(const PlanDev& pd, size_t smem_optin) {
-    return pd.fast_ok && pd.n_mels == 64 && mic_smem_bytes(pd) <= smem_optin;
+    return pd.item_ok && pd.n_mels == 64 && mic_smem_bytes(pd) <= smem_optin;
 }
 
 int mic_frames_per_tile() { return mic::kW; }
