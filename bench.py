@@ -770,7 +770,7 @@ def run_ours(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': cfg2_config(B, world),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'seld::foa_iv2_kernel<8,float,true,false> (+ its redo scan <...,true>, inside the timed step)',
+                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'seld::foa_iv2_kernel<8,float,true,false,true> (item form of the mel step; one launch per step)',
                          'algorithmic_bytes_per_launch': B * ALGO_BYTES_PER_CLIP, 'launch_ms': launch_ms,
                          'fp32_frac': fp32_achieved / fp32_peak, 'fp32_achieved_tflops': fp32_achieved,
                          'fp32_peak_tflops': fp32_peak, 'fp32_peak_source': 'measured here: cuBLAS SGEMM 8192^3, TF32 off (nominal 148 x 128 x 2 x 1.965 GHz = 74.4)',

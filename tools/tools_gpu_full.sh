@@ -11,3 +11,6 @@ for w in cfg3 cfg4 cfg5 wav2img augment; do
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --cpu-seconds 0 > gpurun_out/ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scalar_wav2img -s 5 -c 1 -o gpurun_out/prof_epi python bench.py --workload wav2img --steps 10 --warmup 3 > gpurun_out/ncu_epi.log 2>&1
+# ncu --set full of the two feature kernels (one launch each, after warm-up) -> tools/ncu_summary.py / tools_sass_hot.py read them here
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:foa_iv2 -s 5 -c 1 -f -o gpurun_out/prof_foa_r02 python tools/prof_foa.py > gpurun_out/ncu_foa.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:mic_features -s 5 -c 1 -f -o gpurun_out/prof_mic_r02 python tools/prof_foa.py mic > gpurun_out/ncu_mic.log 2>&1
