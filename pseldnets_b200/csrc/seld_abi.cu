@@ -181,8 +181,34 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                 }
                 return pl;
             };
-            // Search: classes K, longest piece `maxlen`, and `slack` extra positions per class (more freedom for the matching)
-            std::vector<Piece> best; int bestK = 0, bestSlack = 0; long bestCost = -1;
+            // A candidate plan = the pieces of every class and the class lengths (multiples of four: the kernel walks a class
+            // four positions at a time).  Cost per position: 4 loads of `wf` wavefronts, the weights, the per-bin arithmetic;
+            // per class: its sums are stored and read back once.
+            struct Cand { std::vector<std::vector<Piece>> cls; std::vector<int> L; long cost = -1; };
+            auto evaluate = [&](Cand& cd) {
+                int P = 0; long cost = 28L * (long)cd.cls.size();
+                for (size_t c = 0; c < cd.cls.size(); ++c) {
+                    if (cd.cls[c].empty() || cd.cls[c].size() > 32) { cd.cost = -1; return; }
+                    const Place pl = place_class(cd.cls[c], cd.L[c]);
+                    cost += (long)cd.L[c] * (4 * pl.wf + 14);
+                    P += cd.L[c];
+                }
+                cd.cost = (P >= 8 && P <= 24) ? cost : -1;
+            };
+            Cand best;
+            const bool plan_debug = getenv("SELD_PLAN_DEBUG") && atoi(getenv("SELD_PLAN_DEBUG")) > 1;
+            auto consider = [&](Cand& cd) {
+                evaluate(cd);
+                if (plan_debug && cd.cost >= 0) {
+                    fprintf(stderr, "[seld plan] candidate (");
+                    for (size_t c = 0; c < cd.L.size(); ++c) fprintf(stderr, "%s%d x%zu wf%d", c ? ", " : "", cd.L[c], cd.cls[c].size(), place_class(cd.cls[c], cd.L[c]).wf);
+                    fprintf(stderr, ") cost %ld\n", cd.cost);
+                }
+                if (cd.cost >= 0 && (best.cost < 0 || cd.cost < best.cost)) best = cd;
+            };
+            // Near-equal cuts: every segment into ceil(n / maxlen) pieces, the 32 longest pieces form class 0, the next 32 class 1, ...
+            // (Cutting to a tuple of class lengths instead -- (8, 4, 4, 4) = 20 positions fits the reference bank where this gives
+            // (12, 8, 4) = 24 -- was measured 1.2 % SLOWER: a fourth class costs more in stored / re-read sums than four positions.)
             for (int K = 1; K <= 4; ++K)
                 for (int maxlen = 1; maxlen <= 24; ++maxlen) {
                     std::vector<Piece> pc; bool ok = true;
@@ -196,30 +222,23 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                     if (!ok || (int)pc.size() > 32 * K || pc.empty()) continue;
                     std::stable_sort(pc.begin(), pc.end(), [](const Piece& x, const Piece& y) { return x.n > y.n; });
                     for (int slack = 0; slack <= 4; slack += 4) {
-                        long cost = 28L * K; int P = 0;
-                        for (int c = 0; c < K; ++c) {
-                            if ((size_t)(32 * c) >= pc.size()) continue;
-                            std::vector<Piece> cl(pc.begin() + 32 * c, pc.begin() + std::min(pc.size(), (size_t)32 * (c + 1)));
-                            const int L = (cl[0].n + slack + 3) & ~3;   // the kernel walks a class four positions at a time
-                            const Place pl = place_class(cl, L);
-                            cost += (long)L * (7 * pl.wf + 12) / 2;    // per position: 3.5 loads of pl.wf wavefronts, the weights, the arithmetic
-                            P += L;
+                        Cand cd;
+                        for (int c = 0; c < K && (size_t)(32 * c) < pc.size(); ++c) {
+                            cd.cls.emplace_back(pc.begin() + 32 * c, pc.begin() + std::min(pc.size(), (size_t)32 * (c + 1)));
+                            cd.L.push_back((cd.cls.back()[0].n + slack + 3) & ~3);
                         }
-                        if (P > 24) continue;
-                        if (bestCost < 0 || cost < bestCost) { bestCost = cost; best = pc; bestK = K; bestSlack = slack; }
+                        consider(cd);
                     }
                 }
-            if (bestCost >= 0) {
-                iK = bestK;
-                for (int c = 0; c < 4; ++c) { iL[c] = (c < iK && (size_t)(32 * c) < best.size()) ? (best[32 * c].n + bestSlack + 3) & ~3 : 0; }
-                for (int c = 0; c < 4; ++c) { ioff[c] = iP; iP += iL[c]; }
-                if (iP >= 8 && iP <= 24) {
+            if (best.cost >= 0) {
+                iK = (int)best.cls.size();
+                for (int c = 0; c < 4; ++c) { iL[c] = c < iK ? best.L[c] : 0; ioff[c] = iP; iP += iL[c]; }
+                {
                     item_ok = 1;
                     iw.assign((size_t)iP * 32 * 2, 0.0f);
                     std::vector<std::vector<int>> seg_slots(n_mels + 2);
                     for (int c = 0; c < iK; ++c) {
-                        if (iL[c] == 0) continue;
-                        std::vector<Piece> cl(best.begin() + std::min(best.size(), (size_t)32 * c), best.begin() + std::min(best.size(), (size_t)32 * (c + 1)));
+                        const std::vector<Piece>& cl = best.cls[c];
                         const Place pl = place_class(cl, iL[c]);
                         if (getenv("SELD_PLAN_DEBUG")) fprintf(stderr, "[seld plan] class %d: %d positions, %zu pieces, %d wavefronts per 64-bit load\n", c, iL[c], cl.size(), pl.wf);
                         for (int l = 0; l < 32; ++l) {
@@ -234,6 +253,7 @@ extern "C" int seld_plan_create(seld_plan** out, int device, const float* window
                             }
                         }
                     }
+                    for (int sgm = 0; sgm <= n_mels + 1; ++sgm) if (seg_slots[sgm].size() > 4) item_ok = 0;   // cannot happen: <= 4 pieces per segment
                     auto pack = [&](const std::vector<int>& v) {
                         uint32_t r = 0;
                         for (int i = 0; i < 4; ++i) r |= (uint32_t)(i < (int)v.size() ? v[i] : 128) << (8 * i);   // 128: the slot kept at zero

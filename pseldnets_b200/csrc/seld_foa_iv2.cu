@@ -205,6 +205,17 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         if (lane < M) { slotV0 = pack_runs(gseg_s[lane], gseg_s[lane + 1]); slotU0 = pack_runs(gseg_s[lane + 1], gseg_s[lane + 2]); }
         if (lane + 32 < M) { slotV1 = pack_runs(gseg_s[lane + 32], gseg_s[lane + 33]); slotU1 = pack_runs(gseg_s[lane + 33], gseg_s[lane + 34]); }
     }
+    // item form: longest V / U list of the bands of round 0 (bands 0-31) and round 1, four bits each (warp-uniform)
+    int itemCnt = 0;
+    if constexpr (kItem) {
+        auto cnt = [&](uint32_t p) {
+            int n = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) n += ((p >> (8 * i)) & 0xff) != (uint32_t)kItemZero;
+            return __reduce_max_sync(0xffffffffu, n > 0 ? n : 1);
+        };
+        itemCnt = cnt(slotV0) | (cnt(slotU0) << 4) | (cnt(slotV1) << 8) | (cnt(slotU1) << 12);
+    }
     // fourth slot in use by any band?  (warp-uniform; most banks never split a segment over four chunks)
     constexpr uint32_t kAbsent = kItem ? kItemZero : kZeroRun;
     const bool four = __any_sync(0xffffffffu, (slotV0 >> 24) != kAbsent || (slotU0 >> 24) != kAbsent ||
@@ -335,18 +346,31 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                                 const float2* S = reinterpret_cast<const float2*>(R);
                                 const int iv0 = pv & 0xff, iv1 = (pv >> 8) & 0xff, iv2 = (pv >> 16) & 0xff, iv3 = pv >> 24;
                                 const int iu0 = pu & 0xff, iu1 = (pu >> 8) & 0xff, iu2 = (pu >> 16) & 0xff, iu3 = pu >> 24;
+                                // only as many list entries as some band of this round has (warp-uniform counts: the low bands
+                                // are one or two pieces each, the high ones up to four)
+                                const int nv = (r ? itemCnt >> 8 : itemCnt) & 15, nu = (r ? itemCnt >> 12 : itemCnt >> 4) & 15;
 #pragma unroll
                                 for (int f = 0; f < (kIV ? 3 : 2); ++f) {
                                     const float2* su = S + (2 * f) * kItemSlots;
                                     const float2* sv = su + kItemSlots;
-                                    const float2 v0 = sv[iv0], v1 = sv[iv1], v2 = sv[iv2], u0 = su[iu0], u1 = su[iu1], u2 = su[iu2];
-                                    if constexpr (kFour) vv[f] = vadd(vadd(vadd(v0, v1), vadd(v2, sv[iv3])), vadd(vadd(u0, u1), vadd(u2, su[iu3])));
-                                    else vv[f] = vadd(vadd(vadd(v0, v1), v2), vadd(vadd(u0, u1), u2));
+                                    float2 acc = vadd(sv[iv0], su[iu0]);
+                                    if (nv > 1) acc = vadd(acc, sv[iv1]);
+                                    if (nu > 1) acc = vadd(acc, su[iu1]);
+                                    if (nv > 2) acc = vadd(acc, sv[iv2]);
+                                    if (nu > 2) acc = vadd(acc, su[iu2]);
+                                    if (nv > 3) acc = vadd(acc, sv[iv3]);
+                                    if (nu > 3) acc = vadd(acc, su[iu3]);
+                                    vv[f] = acc;
                                 }
                                 if constexpr (kIV) {
                                     const float2* s3 = S + 6 * kItemSlots;
-                                    float t3 = ((s3[iv0].y + s3[iv1].y) + s3[iv2].y) + ((s3[iu0].x + s3[iu1].x) + s3[iu2].x);
-                                    if constexpr (kFour) t3 += s3[iv3].y + s3[iu3].x;
+                                    float t3 = s3[iv0].y + s3[iu0].x;
+                                    if (nv > 1) t3 += s3[iv1].y;
+                                    if (nu > 1) t3 += s3[iu1].x;
+                                    if (nv > 2) t3 += s3[iv2].y;
+                                    if (nu > 2) t3 += s3[iu2].x;
+                                    if (nv > 3) t3 += s3[iv3].y;
+                                    if (nu > 3) t3 += s3[iu3].x;
                                     vv[NP - 1] = make_float2(t3, 0.0f);
                                 }
                             } else {

@@ -286,6 +286,25 @@ def test_other_configurations_against_oracle():
         pb.LogmelIV_Extractor(make_cfg(24000, 240, nfft=512)).cuda()(torch.zeros(1, 4, 2400, device='cuda'))
 
 
+@pytest.mark.parametrize('kind', ['logmelIV', 'logmel'])
+def test_mel_banks_of_many_shapes_against_oracle(kind):
+    """The mel step's item form is planned per bank (pieces of segments, classes, matched first bins): banks with few
+    wide bands (pieces of 12+ bins, or no item form at all and the run form instead), many narrow ones, and low sample
+    rates where the top bands are a few bins wide."""
+    from oracle import seld_oracle as so, synth
+    for sr, hop, n_mels in ((24000, 240, 8), (24000, 240, 16), (24000, 240, 20), (24000, 240, 32), (24000, 240, 48), (24000, 240, 63),
+                            (8000, 80, 64), (8000, 80, 24), (32000, 320, 56), (48000, 480, 33)):
+        cfg = make_cfg(sr, hop, 'hann', kind, n_mels=n_mels)
+        ext = (pb.LogmelIV_Extractor if kind == 'logmelIV' else pb.Logmel_Extractor)(cfg).cuda()
+        C = 4 if kind == 'logmelIV' else 3
+        x = synth.white(900 + n_mels + hop, 2, C, 13 * hop + 7)
+        y = _run(ext, x)
+        fn = so.logmel_iv if kind == 'logmelIV' else so.logmel
+        ref = fn(x, ext.stft_extractor.window.cpu().numpy(), ext.mel_scale.fb.cpu().numpy(), 1024, hop, np.float64)
+        assert y.shape == ref.shape
+        assert_blocks_close(y, ref, C, what='%s sr=%d M=%d' % (kind, sr, n_mels))
+
+
 def test_fuzz_shapes_against_oracle():
     """Seeded sweep over awkward shapes: shortest legal clip (L = 513), single-frame outputs, hops that are
     odd / larger than the window, batch sizes around the tile size, unaligned lengths."""
