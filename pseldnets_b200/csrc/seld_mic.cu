@@ -281,11 +281,15 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     pr = zr; pi = zi;
                 } else {
                     constexpr int pp = brev5(31 - kb), p0 = brev5((32 - kb) & 31);
+#ifdef MABL_NOSHFL
+                    pr = re[pp]; pi = im[pp];
+#else
                     pr.x = __shfl_sync(0xffffffffu, re[pp].x, src);
                     pr.y = __shfl_sync(0xffffffffu, re[pp].y, src);
                     pi.x = __shfl_sync(0xffffffffu, im[pp].x, src);
                     pi.y = __shfl_sync(0xffffffffu, im[pp].y, src);
                     if (lane == 0) { pr = re[p0]; pi = im[p0]; }
+#endif
                 }
                 ar = vadd(zr, pr); ai = vsub(zi, pi);
                 br = vadd(zi, pi); bi = vsub(pr, zr);
@@ -320,14 +324,23 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             if (kb < 16 || lane == 0) {
                 const int k = lane + 32 * kb;
                 // PHAT only needs phases: keep X_c / |X_c| (unit phasors) for the GCC passes
+#ifdef MABL_NOINVMAG
+                const float2 n02 = p02, n13 = p13;
+#else
                 const float2 n02 = make_float2(inv_mag(p02.x), inv_mag(p02.y)), n13 = make_float2(inv_mag(p13.x), inv_mag(p13.y));
                 min_n = fminf(min_n, fminf(fminf(n02.x, n02.y), fminf(n13.x, n13.y)));
+#endif
                 const float2 ur02 = __fmul2_rn(ar, n02), ui02 = __fmul2_rn(ai, n02);
                 const float2 ur13 = __fmul2_rn(br, n13), ui13 = __fmul2_rn(bi, n13);
+#ifdef MABL_NOSPECST
+                if (__float_as_uint(ur02.x + ui02.x + ur13.x + ui13.x + ur02.y + ui02.y + ur13.y + ui13.y) == 0x12345678u)
+#endif
+                {
                 spec[0 * kSpecStride + k] = make_float2(ur02.x, ui02.x);
                 spec[1 * kSpecStride + k] = make_float2(ur13.x, ui13.x);
                 spec[2 * kSpecStride + k] = make_float2(ur02.y, ui02.y);
                 spec[3 * kSpecStride + k] = make_float2(ur13.y, ui13.y);
+                }
                 reinterpret_cast<float2*>(R)[k] = p02;                      // pair rows (P0, P2), (P1, P3) in natural bin order
                 reinterpret_cast<float2*>(R)[kItemRow + k] = p13;
             }
