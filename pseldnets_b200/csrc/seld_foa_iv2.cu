@@ -82,6 +82,53 @@ __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// ---- tensor memory as a second, lane-private table store.  The window, twiddle and mel-weight tables are indexed by lane:
+// lane l only ever reads its own entries.  Tensor memory (tcgen05.ld / st, 128 lanes x 512 columns x 32 bit per SM, a warp
+// reaches the 32 lanes of its quarter) serves exactly that pattern through its own datapath, which leaves the shared-memory /
+// L1 data pipe -- the pipe this kernel is bound by -- to the transposes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+        :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+           "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+           "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+           "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ... for loads issued ahead of their use: the wait "rewrites" the destination registers, so no read of them can be scheduled
+// before it (the hardware may write them until the wait returns)
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+}
+constexpr uint32_t kTmemCols = 256;       // columns allocated: window [0, 32), twiddles [32, 96), mel weights [96, 96 + 2 iP)
+#ifndef SELD_NO_TMEM_TABLES
+#define SELD_TMEM_TABLES 1
+#endif
+
 // TIn = float (the reference's input) or int16_t (PCM as decoded from wav/flac: soundfile's float32
 // conversion is s / 32768, folded exactly into the window: a.in_scale = 2^-15)
 // kIV = true : one warp = one frame of a 4-channel clip -> 4 log-mel + 3 IV rows (LogmelIV_Extractor).
@@ -164,7 +211,51 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         for (int i = tid; i < pd.n_mels + 2; i += W * 32) gseg_s[i] = pd.gseg[i];
     }
     if (tid == 0) *marked_s = 0;
+    uint32_t tmem_w = 0;                                                    // item form: tensor-memory address of this warp's lane quarter, column 0
+#ifdef SELD_TMEM_TABLES
+    if constexpr (kItem) {
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(marked_s + 1);
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_w = *tmem_slot + ((uint32_t)(warp & 3) << 21);               // lane field = 32 * (warp % 4), bits 31:16
+        if (warp < 4) {                                                     // one copy of the tables per lane quarter (warps w and w + 4 share it)
+            uint32_t v[32];
+#pragma unroll
+            for (int m = 0; m < 32; ++m) v[m] = __float_as_uint(pd.win[32 * m + lane] * in_scale);
+            tmem_st32(tmem_w, v);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                                   // positions 16 h .. 16 h + 15: (cos, -sin) pairs
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const float2 w = pd.tw[brev5(16 * h + r) * 32 + lane];
+                    v[2 * r] = __float_as_uint(w.x); v[2 * r + 1] = __float_as_uint(w.y);
+                }
+                tmem_st32(tmem_w + 32 + 32 * h, v);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                                   // mel weights (a, b) of positions 16 h .. 16 h + 15
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int pos = 16 * h + r;
+                    const float2 w = pos < pd.iP ? pd.iw[pos * 32 + lane] : make_float2(0.0f, 0.0f);
+                    v[2 * r] = __float_as_uint(w.x); v[2 * r + 1] = __float_as_uint(w.y);
+                }
+                tmem_st32(tmem_w + 96 + 32 * h, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+#endif
     __syncthreads();
+#ifdef SELD_TMEM_TABLES
+    if constexpr (kItem) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
 
     float* R = R_all + warp * region;
     float2* scratch = reinterpret_cast<float2*>(R);
@@ -557,6 +648,18 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             }
         }
 #endif
+#ifdef SELD_TMEM_TABLES
+        if constexpr (kItem) {
+            uint32_t wv[32];
+            tmem_ld32(tmem_w, wv);
+            tmem_wait_ld(wv);
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                re[m] = vmuls(re[m], __uint_as_float(wv[m]));
+                im[m] = vmuls(im[m], __uint_as_float(wv[m]));
+            });
+        } else
+#endif
 #ifndef ABL_NOWIN
         static_for<0, 8>([&](auto mi) {
             constexpr int m4 = decltype(mi)::value;
@@ -576,6 +679,29 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         fft32(re, im);
 #endif
         PHASE_MARK(3);   // first 32-pt
+#ifdef SELD_TMEM_TABLES
+        if constexpr (kItem) {
+            static_for<0, 2>([&](auto hi) {
+                constexpr int h = decltype(hi)::value;
+                uint32_t tv[32];
+                tmem_ld32(tmem_w + 32 + 32 * h, tv);
+                tmem_wait_ld(tv);
+                static_for<0, 8>([&](auto qi) {
+                    constexpr int p2 = 8 * h + decltype(qi)::value;         // positions 2*p2, 2*p2+1
+                    constexpr int o = 4 * decltype(qi)::value;
+                    const float wx = __uint_as_float(tv[o]), wy = __uint_as_float(tv[o + 1]), wz = __uint_as_float(tv[o + 2]), ww = __uint_as_float(tv[o + 3]);
+                    if constexpr (p2 > 0) {                                 // position 0 is ka = 0: twiddle 1
+                        const float2 r = re[2 * p2], i = im[2 * p2];
+                        re[2 * p2] = vfmas(i, -wy, vmuls(r, wx));
+                        im[2 * p2] = vfmas(i, wx, vmuls(r, wy));
+                    }
+                    const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
+                    re[2 * p2 + 1] = vfmas(i, -ww, vmuls(r, wz));
+                    im[2 * p2 + 1] = vfmas(i, wz, vmuls(r, ww));
+                });
+            });
+        } else
+#endif
 #ifndef ABL_NOTW
         static_for<0, 16>([&](auto pi) {
             constexpr int p2 = decltype(pi)::value;                         // positions 2*p2, 2*p2+1
@@ -710,11 +836,23 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 const float2* zp = Q + ist[c];
                 const float2* wp = iw_s + 32 * pd.ioff[c] + lane;
 #pragma unroll 1
-                for (int j0 = 0; j0 < Lc; j0 += 4)                          // class lengths are multiples of four: no remainder code
+                for (int j0 = 0; j0 < Lc; j0 += 4) {                        // class lengths are multiples of four: no remainder code
+#ifdef SELD_TMEM_TABLES
+                // the four weight pairs of this trip, from tensor memory.  (Asking for them one trip ahead, or for the window
+                // before the global loads, was measured 17 % SLOWER: registers a tcgen05.ld has been told to write must not be
+                // touched until the wait, and tying them to the wait costs copies and spills.)
+                uint32_t w8[8];
+                tmem_ld8(tmem_w + 96 + 2 * (pd.ioff[c] + j0), w8);
+                tmem_wait_ld(w8);
+#endif
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj, ++zp, wp += 32) {
                     const float2 zr = zp[0], zi = zp[kItemRow], pr = zp[2 * kItemRow], pi = zp[3 * kItemRow];
+#ifdef SELD_TMEM_TABLES
+                    const float2 w = make_float2(__uint_as_float(w8[2 * jj]), __uint_as_float(w8[2 * jj + 1]));
+#else
                     const float2 w = *wp;
+#endif
                     // window was pre-scaled by 0.5: A = Z[k] + conj(Z[N-k]), B = (Z[k] - conj(Z[N-k])) / i
                     const float2 ar = vadd(zr, pr), ai = vsub(zi, pi);      // (X0, X2)
                     const float2 br = vadd(zi, pi), bi = vsub(pr, zr);      // (X1, X3)
@@ -733,6 +871,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                         aU[c][2] = __ffma2_rn(aa, n13, aU[c][2]); aV[c][2] = __ffma2_rn(bb, n13, aV[c][2]);
                         a3[c] = __ffma2_rn(w, make_float2(n2, n2), a3[c]);
                     }
+                }
                 }
             });
             __syncwarp();                                                   // every lane is through with the rows: the sums may overwrite them
@@ -768,7 +907,15 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         __syncwarp();                                                       // rows are reused by the next frame's exchange
         PHASE_MARK(8);   // mel combine + store
     }
+#ifdef SELD_TMEM_TABLES
+    if constexpr (kItem) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
     __syncthreads();
+#ifdef SELD_TMEM_TABLES
+    if constexpr (kItem) {
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_w), "r"(kTmemCols));
+    }
+#endif
     if (tid == 0) {
         // the last block to finish launches the redo grid if any block marked a frame (one launch, all SMs; tail launches of
         // single blocks would run one after the other)
