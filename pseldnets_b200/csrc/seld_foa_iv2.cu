@@ -24,6 +24,7 @@
 
 #include "fft32.cuh"
 #include "seld_plan.h"
+#include "tmem_tables.cuh"
 
 #ifndef SELD_STRIDED_TILES
 #define SELD_CONTIG 1      // a block owns a contiguous range of tiles (measured -3 % against grid-stride tiles: neighbouring tiles share samples in L1)
@@ -81,53 +82,6 @@ constexpr uint32_t kRedoMark = 0x7fc5e1d0u;   // quiet NaN with a payload
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-// ---- tensor memory as a second, lane-private table store.  The window, twiddle and mel-weight tables are indexed by lane:
-// lane l only ever reads its own entries.  Tensor memory (tcgen05.ld / st, 128 lanes x 512 columns x 32 bit per SM, a warp
-// reaches the 32 lanes of its quarter) serves exactly that pattern through its own datapath, which leaves the shared-memory /
-// L1 data pipe -- the pipe this kernel is bound by -- to the transposes.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
-        :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-           "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
-           "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
-           "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// ... for loads issued ahead of their use: the wait "rewrites" the destination registers, so no read of them can be scheduled
-// before it (the hardware may write them until the wait returns)
-__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
-                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
-                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
-                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) :: "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
-}
-constexpr uint32_t kTmemCols = 256;       // columns allocated: window [0, 32), twiddles [32, 96), mel weights [96, 96 + 2 iP)
-#ifndef SELD_NO_TMEM_TABLES
-#define SELD_TMEM_TABLES 1
-#endif
 
 // TIn = float (the reference's input) or int16_t (PCM as decoded from wav/flac: soundfile's float32
 // conversion is s / 32768, folded exactly into the window: a.in_scale = 2^-15)
@@ -214,15 +168,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     uint32_t tmem_w = 0;                                                    // item form: tensor-memory address of this warp's lane quarter, column 0
 #ifdef SELD_TMEM_TABLES
     if constexpr (kItem) {
-        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(marked_s + 1);
-        if (warp == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tmem_w = *tmem_slot + ((uint32_t)(warp & 3) << 21);               // lane field = 32 * (warp % 4), bits 31:16
+        tmem_w = tmem_tables_alloc(reinterpret_cast<uint32_t*>(marked_s + 1), warp);
         if (warp < 4) {                                                     // one copy of the tables per lane quarter (warps w and w + 4 share it)
             uint32_t v[32];
 #pragma unroll
@@ -913,7 +859,7 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     __syncthreads();
 #ifdef SELD_TMEM_TABLES
     if constexpr (kItem) {
-        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_w), "r"(kTmemCols));
+        tmem_tables_free(tmem_w, warp);
     }
 #endif
     if (tid == 0) {

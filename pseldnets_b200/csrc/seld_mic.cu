@@ -27,6 +27,18 @@
 #include "fft32.cuh"
 #include "mel_seg.cuh"
 #include "seld_plan.h"
+#include "tmem_tables.cuh"
+
+// the 64 twiddle floats of the lane, (cos, cos', -sin, -sin') per pair of positions: from tensor memory (two loads, then
+// compile-time indexing) or from the shared-memory table
+#ifdef SELD_TMEM_TABLES
+#define TW_FETCH() uint32_t tvA[32], tvB[32]; tmem_ld32(tmem_w + 32, tvA); tmem_ld32(tmem_w + 64, tvB); tmem_wait_ld(tvA); tmem_wait_ld(tvB)
+#define TW4(p2) make_float4(__uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7)]), __uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7) + 1]), \
+                            __uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7) + 2]), __uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7) + 3]))
+#else
+#define TW_FETCH() do { } while (0)
+#define TW4(p2) (*reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * (p2)))
+#endif
 
 namespace seld {
 namespace mic {
@@ -101,7 +113,43 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     }
     for (int i = tid; i < 64 * pd.iP; i += W * 32) wab_s[i] = reinterpret_cast<const float*>(pd.iw)[i];
     if (tid == 0) *marked_s = 0;
+    // the lane-private tables also go to tensor memory (tmem_tables.cuh): window [0, 32), twiddles in this kernel's layout
+    // [32, 96), mel weights [96, 96 + 2 iP); the loop reads them from there, off the shared-memory pipe
+    uint32_t tmem_w = 0;
+#ifdef SELD_TMEM_TABLES
+    tmem_w = tmem_tables_alloc(reinterpret_cast<uint32_t*>(marked_s + 1), warp);
+    if (warp < 4) {
+        uint32_t v[32];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) v[m] = __float_as_uint(pd.win[32 * m + lane]);
+        tmem_st32(tmem_w, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                                       // positions 16 h .. 16 h + 15 as (cos, cos', -sin, -sin') per pair
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const float2 w = pd.tw[brev5(16 * h + r) * 32 + lane];
+                v[4 * (r >> 1) + (r & 1)] = __float_as_uint(w.x); v[4 * (r >> 1) + 2 + (r & 1)] = __float_as_uint(w.y);
+            }
+            tmem_st32(tmem_w + 32 + 32 * h, v);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int pos = 16 * h + r;
+                const float2 w = pos < pd.iP ? pd.iw[pos * 32 + lane] : make_float2(0.0f, 0.0f);
+                v[2 * r] = __float_as_uint(w.x); v[2 * r + 1] = __float_as_uint(w.y);
+            }
+            tmem_st32(tmem_w + 96 + 32 * h, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
     __syncthreads();
+#ifdef SELD_TMEM_TABLES
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
 
     float2* spec = reinterpret_cast<float2*>(R_all + warp * kRegion);      // [4][kSpecStride]
     float* R = R_all + warp * kRegion + kSpec;                             // 4 rows / exchange buffer
@@ -217,6 +265,18 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 im[m] = in ? make_float2(__ldg(p + a.stride_c), __ldg(p + 3 * a.stride_c)) : make_float2(0.f, 0.f);
             });
         }
+#ifdef SELD_TMEM_TABLES
+        {
+            uint32_t wv[32];
+            tmem_ld32(tmem_w, wv);
+            tmem_wait_ld(wv);
+            static_for<0, 32>([&](auto mi) {
+                constexpr int m = decltype(mi)::value;
+                re[m] = vmuls(re[m], __uint_as_float(wv[m]));
+                im[m] = vmuls(im[m], __uint_as_float(wv[m]));
+            });
+        }
+#else
         static_for<0, 8>([&](auto mi) {
             constexpr int m4 = decltype(mi)::value;
             const float4 w4 = *reinterpret_cast<const float4*>(win_s + lane * kWinStride + 4 * m4);
@@ -227,12 +287,14 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 im[4 * m4 + e] = vmuls(im[4 * m4 + e], w[e]);
             }
         });
+#endif
 
         // ---------------- forward: two 1024-point FFTs at once
         fft32(re, im);
+        TW_FETCH();
         static_for<0, 16>([&](auto pi) {
             constexpr int p2 = decltype(pi)::value;                         // positions 2*p2, 2*p2+1
-            const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
+            const float4 w4 = TW4(p2);
             if constexpr (p2 > 0) {
                 const float2 r = re[2 * p2], i = im[2 * p2];
                 re[2 * p2] = vfmas(i, -w4.z, vmuls(r, w4.x));
@@ -364,13 +426,24 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     const float2* qp = Q + ist[c];
                     const float2* wp = iw_s + 32 * pd.ioff[c] + lane;
 #pragma unroll 1
-                    for (int j0 = 0; j0 < Lc; j0 += 4)                      // class lengths are multiples of four
+                    for (int j0 = 0; j0 < Lc; j0 += 4) {                    // class lengths are multiples of four
+#ifdef SELD_TMEM_TABLES
+                    uint32_t w8[8];
+                    tmem_ld8(tmem_w + 96 + 2 * (pd.ioff[c] + j0), w8);
+                    tmem_wait_ld(w8);
+#endif
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj, ++qp, wp += 32) {
-                        const float2 q0 = qp[0], q1 = qp[kItemRow], w = *wp;
+                        const float2 q0 = qp[0], q1 = qp[kItemRow];
+#ifdef SELD_TMEM_TABLES
+                        const float2 w = make_float2(__uint_as_float(w8[2 * jj]), __uint_as_float(w8[2 * jj + 1]));
+#else
+                        const float2 w = *wp;
+#endif
                         const float2 aa = make_float2(w.x, w.x), bb = make_float2(w.y, w.y);
                         aU[c][0] = __ffma2_rn(aa, q0, aU[c][0]); aV[c][0] = __ffma2_rn(bb, q0, aV[c][0]);
                         aU[c][1] = __ffma2_rn(aa, q1, aU[c][1]); aV[c][1] = __ffma2_rn(bb, q1, aV[c][1]);
+                    }
                     }
                 });
             }
@@ -483,9 +556,10 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             if (any_zero) build(std::true_type{}); else build(std::false_type{});
             // inverse 32-point stage over m: swap(FFT(swap(z)))
             fft32(im, re);                                                  // position p: A[lane][n2 = brev5(p)]
+            TW_FETCH();
             static_for<0, 16>([&](auto pi) {                                // table holds (cos, -sin): multiply by (cos + i sin)
                 constexpr int p2 = decltype(pi)::value;
-                const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 4 * p2);
+                const float4 w4 = TW4(p2);
                 if constexpr (p2 > 0) {
                     const float2 r = re[2 * p2], i = im[2 * p2];
                     re[2 * p2] = vfmas(i, w4.z, vmuls(r, w4.x));
@@ -556,11 +630,12 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             fft32_dit(zi, zr);                                              // position q': (A[lane][q], A[lane][q + 16]), q = brev4(q')
             float* fr = R;                                                  // two planes of 32 x 34 floats in the exchange area
             float* fi = R + 32 * kXStride;
+            TW_FETCH();
             static_for<0, 16>([&](auto qi) {
                 constexpr int qp = decltype(qi)::value;
                 constexpr int q = brev4(qp);
                 // table positions brev5(q) (even) and brev5(q + 16) = brev5(q) + 1 share one float4: (cos, cos', -sin, -sin')
-                const float4 w4 = *reinterpret_cast<const float4*>(tw_s + lane * kTwStride + 2 * brev5(q));
+                const float4 w4 = TW4(brev5(q) / 2);
                 float2 r = zr[qp], i = zi[qp];
                 if constexpr (q == 0) {                                     // W^0 = 1 for n2 = 0; n2 = 16 still needs its factor
                     const float r1 = r.y, i1 = i.y;
@@ -597,6 +672,11 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
 #endif
     }
     flush_max();
+#ifdef SELD_TMEM_TABLES
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    tmem_tables_free(tmem_w, warp);
+#endif
     if constexpr (kMode == 0 && !kRedo) {
         // a block that marked frames launches the redo form for them into the tail of this grid: it runs when the whole
         // grid is done and before the stream's next kernel (the top_db floor)
