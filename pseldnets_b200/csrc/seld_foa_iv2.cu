@@ -10,12 +10,18 @@
 //   * samples are read straight from global memory with coalesced 128-byte warp loads (the
 //     1024-hop overlap of neighbouring frames is served by L1/L2) -> no staging buffer, no
 //     __syncthreads, no exposed staging latency;
-//   * all seven per-bin quantities of the frame are produced in one pass and written to seven
-//     swizzled shared-memory rows; the mel projection walks them ONCE: lane c owns bins
-//     [16c, 16c+16), accumulates per mel "segment" (the bins between two consecutive band
-//     centres feed exactly bands s-1 and s) as one FFMA2 per bin and feature, and leaves per-run
-//     partial sums that a second, band-per-lane step combines (out[m] = V[m] + U[m+1]).
-//     Conflict-free 128-bit reads, balanced lanes, 2 weights per bin instead of a band table.
+//   * the mel step.  For a triangular bank every bin feeds exactly two bands: the bins between two consecutive band
+//     centres (a "segment" s) feed bands s-1 and s, so out[m] = V[m] + U[m+1] with U / V the a- / b-weighted sums of a
+//     segment.  Two forms of it live in this file:
+//       - ITEM form (kItem = true; main form of both modes, round 2): the packed spectra go to shared memory as they leave
+//         the transform (natural bin order, bin 1024 - k beside bin k), and every lane walks one PIECE of a segment per
+//         class, doing the untangle / power / IV arithmetic of a bin and the seven weighted accumulates in one go -- one
+//         instruction stream for all lanes, no run boundaries, no shuffles (see the comment at the kernel);
+//       - RUN form (kItem = false; round 1; the redo form and banks the item plan does not fit): the seven per-bin
+//         quantities are written to swizzled rows, lane c owns bins [16c, 16c+16) and accumulates per run of one segment,
+//         with predicated partial-sum stores at the run boundaries.
+//     Both end in a band-per-lane combine step that adds up at most four partial sums per list.
+//   * the lane-private tables (window, twiddles, mel weights) of the item form live in tensor memory (tmem_tables.cuh).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
