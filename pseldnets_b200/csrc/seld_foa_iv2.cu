@@ -877,11 +877,15 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             __threadfence();
             const int any = atomicExch(&a.redo_flags[1], 0);
             atomicExch(&a.redo_flags[0], 0);                               // ready for the next launch that is handed this pair
+#ifndef SELD_NO_DEVICE_LAUNCH                                               // (sanitizer builds: racecheck / synccheck do not support device-side launches)
             if (any) {
                 FoaArgs ar = a;
                 ar.redo_grid = (int)gridDim.x;
                 foa_iv2_kernel<W, TIn, kIV, true><<<gridDim.x, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd);
             }
+#else
+            (void)any;
+#endif
         }
     }
 

@@ -688,11 +688,15 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 __threadfence();
                 const int any = atomicExch(&a.redo_flags[1], 0);
                 atomicExch(&a.redo_flags[0], 0);
+#ifndef SELD_NO_DEVICE_LAUNCH
                 if (any) {
                     FoaArgs ar = a;
                     ar.redo_grid = (int)gridDim.x;
                     mic_features_kernel<0, true><<<gridDim.x, W * 32, a.smem_bytes, cudaStreamTailLaunch>>>(ar, pd, maxkey);
                 }
+#else
+                (void)any;
+#endif
             }
         }
     }

@@ -11,6 +11,9 @@ print('iv i16', iv((x * 20000).to(torch.int16)).abs().sum().item())
 print('iv 8ch', iv(0.1 * torch.randn(1, 8, 3000, device='cuda')).abs().sum().item())
 lm = pb.get_afextractor(cfg('logmel')).cuda(); print('lm', lm(0.1 * torch.randn(3, 3, 2900, device='cuda')).abs().sum().item())
 mic = pb.get_afextractor(cfg('logmelgcc')).cuda(); print('mic', mic(x).abs().sum().item())
+# unbalanced transform partners: frames are marked and redone by the grid the last block launches from the device
+xd = x.clone(); xd[0, 1] = 0.0; xd[1, 2] *= 1e-6
+print('iv redo', iv(xd).abs().sum().item(), 'mic redo', mic(xd).abs().sum().item(), 'lm redo', lm(xd[:, :3]).abs().sum().item())
 iv.mel_scale.fb.copy_(torch.rand(513, 64, device='cuda') * 0.01); print('dense fb (general kernel)', iv(x).abs().sum().item())
 iv = pb.get_afextractor(cfg('logmelIV')).cuda()
 # backbone-input stage: partial tiles in both directions, crop, general scalar kernel
