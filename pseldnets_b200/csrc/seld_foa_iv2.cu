@@ -510,12 +510,18 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             const int Cj = a.C - a.c_lo;
             const int64_t J = (int64_t)a.T * Cj;
             if ((int64_t)4 * grp >= J) continue;
+            // job j = 4 grp + k -> (frame j / Cj, channel j % Cj): ONE division per group, the other three jobs by counting on
+            // (four 64-bit divisions and remainders per group were 11 % of this mode's time)
+            const int64_t j0 = (int64_t)4 * grp;
+            int tq, cq;
+            if (J <= 0x7fffffff) { tq = (int)((uint32_t)j0 / (uint32_t)Cj); cq = (int)((uint32_t)j0 - (uint32_t)tq * (uint32_t)Cj); }
+            else { tq = (int)(j0 / Cj); cq = (int)(j0 - (int64_t)tq * Cj); }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int64_t j = (int64_t)4 * grp + k;
-                vk[k] = j < J;
-                tk[k] = vk[k] ? (int)(j / Cj) : 0;
-                ck[k] = a.c_lo + (vk[k] ? (int)(j % Cj) : 0);
+                vk[k] = j0 + k < J;
+                tk[k] = vk[k] ? tq : 0;
+                ck[k] = a.c_lo + (vk[k] ? cq : 0);
+                if (++cq == Cj) { cq = 0; ++tq; }
             }
         }
         const int t = grp;                                                  // kIV: the frame
