@@ -379,3 +379,27 @@ def test_bench_prints_one_json_line_with_the_contract_keys():
     assert 0 < e['value'] < d['value'] and e['matches_resident_path'] is True
     assert d['gpu_launches'] == 20 and 'workload' in d['config'] and d['outputs_finite'] is True
     assert d['clocks']['sm_mhz'] and d['clocks']['samples'] >= 1
+
+
+def test_concurrent_streams_and_modules_do_not_interact():
+    """Several extractors launched back to back on different streams (FOA, log-mel only, MIC; each block holds its tables in
+    tensor memory and every launch gets its own pair of redo flags): results equal the ones computed one after the other, bit for
+    bit -- also for inputs whose frames are marked and redone by the device-launched grid."""
+    from oracle import synth
+    iv = _ext('logmelIV', 24000, 240, 'hann')
+    lm = _ext('logmel', 24000, 240, 'hann')
+    mic = pb.LogmelGCC_Extractor(make_cfg(24000, 240, 'hann', 'logmelgcc')).cuda()
+    x = torch.from_numpy(synth.white(77, 6, 4, 24000)).cuda()
+    xd = x.clone(); xd[1, 1] = 0.0; xd[3, 2] *= 1e-6                      # a dead and a 120 dB quiet channel: redo path
+    ref = [iv(x), lm(x[:, :3].contiguous()), mic(x), iv(xd), mic(xd)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(5)]
+    for rep in range(3):
+        out = [None] * 5
+        for i, (m, inp) in enumerate(((iv, x), (lm, x[:, :3].contiguous()), (mic, x), (iv, xd), (mic, xd))):
+            streams[i].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[i]):
+                out[i] = m(inp)
+        torch.cuda.synchronize()
+        for i in range(5):
+            assert torch.equal(out[i], ref[i]), (rep, i)
