@@ -80,7 +80,7 @@ int seld_logmel_f32(const seld_plan* plan, const float* x, int64_t B, int C, int
  * GCC-PHAT planes of mic pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3), lags [-n_mels/2, n_mels/2).
  * Frames use librosa.stft's zero ('constant') centre padding.  The plan's fb is the mel bank
  * (librosa.filters.mel(sr, n_fft, n_mels).T).  `workspace` is device scratch of at least
- * seld_workspace_bytes(plan, B, C) bytes (per-plane running maxima). */
+ * seld_workspace_bytes(plan, B, C) bytes (per-plane running maxima and minima). */
 int64_t seld_num_frames_mic(const seld_plan* plan, int64_t L);
 size_t seld_workspace_bytes(const seld_plan* plan, int64_t B, int C);
 int seld_logmel_gcc_f32(const seld_plan* plan, const float* x, int64_t B, int C, int64_t L,

@@ -626,7 +626,7 @@ extern "C" int64_t seld_num_frames_mic(const seld_plan* p, int64_t L) {
 
 extern "C" size_t seld_workspace_bytes(const seld_plan* p, int64_t B, int C) {
     if (!p || B < 0 || C < 1) return 0;
-    return (size_t)B * (size_t)C * sizeof(int);
+    return 2 * (size_t)B * (size_t)C * sizeof(int);                     // per plane: running maximum and minimum
 }
 
 extern "C" int seld_logmel_gcc_f32(const seld_plan* p, const float* x, int64_t B, int C, int64_t L,

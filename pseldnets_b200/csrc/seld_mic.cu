@@ -170,6 +170,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
 
     int cur_b = -1;
     float rmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    float rmin[4] = {INFINITY, INFINITY, INFINITY, INFINITY};               // ... and minima: a plane whose minimum is above its floor is left alone
     auto flush_max = [&]() {
         if (kMode == 1 || cur_b < 0) return;                               // spectrogram mode: no dB planes, no maxima
 #pragma unroll
@@ -179,6 +180,11 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
             if (lane == 0) atomicMax(maxkey + cur_b * 4 + c, f2key(v));
             rmax[c] = -INFINITY;
+            float u = rmin[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) u = fminf(u, __shfl_xor_sync(0xffffffffu, u, o));
+            if (lane == 0) atomicMin(maxkey + (a.B + cur_b) * 4 + c, f2key(u));
+            rmin[c] = INFINITY;
         }
     };
 
@@ -463,9 +469,9 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             // band per lane; run numbers of segment m (V) and m+1 (U) in fixed slots (absent -> the zero run), all
             // loads issued up front (n_mels == 64 on this path: bands lane and lane + 32)
             bool bad = false;                                               // some microphone too far under its transform partner
-            float rmax0[4];                                                 // the maxima before this frame (a marked frame must not count)
+            float rmax0[4], rmin0[4];                                       // the extrema before this frame (a marked frame must not count)
 #pragma unroll
-            for (int f = 0; f < 4; ++f) rmax0[f] = rmax[f];
+            for (int f = 0; f < 4; ++f) { rmax0[f] = rmax[f]; rmin0[f] = rmin[f]; }
             auto unbalanced = [](const float (&v)[4], float t) {
                 return v[0] < t * v[1] || v[1] < t * v[0] || v[2] < t * v[3] || v[3] < t * v[2];
             };
@@ -505,6 +511,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     for (int f = 0; f < 4; ++f) {
                         const float db = 3.01029995663981195f * lg2_ftz(fmaxf(v[f], amin));
                         rmax[f] = fmaxf(rmax[f], db);
+                        rmin[f] = fminf(rmin[f], db);
                         ob[f * ch_stride + m] = db;
                     }
                 }
@@ -516,7 +523,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     // leave the frame to the redo launch: mark it, take its values back out of the running maxima
                     if (lane == 0) { ob[0] = __uint_as_float(kRedoMark); *marked_s = 1; }   // lane 0 wrote that element itself: program order
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) rmax[f] = rmax0[f];
+                    for (int f = 0; f < 4; ++f) { rmax[f] = rmax0[f]; rmin[f] = rmin0[f]; }
                     continue;
                 }
             }
@@ -707,9 +714,10 @@ __global__ void mic_topdb_kernel(float* __restrict__ out, const int* __restrict_
                                  int64_t plane, float top_db) {
     const int bc = blockIdx.y;                                             // b * 4 + c
     const int b = bc >> 2, c = bc & 3;
-    const int key = maxkey[bc];
+    const int key = maxkey[bc], kmin = maxkey[4 * B + bc];
     const float mx = __int_as_float(key >= 0 ? key : key ^ 0x7fffffff);
     const float floor_db = mx - top_db;
+    if (__int_as_float(kmin >= 0 ? kmin : kmin ^ 0x7fffffff) >= floor_db) return;   // nothing in this plane lies under the floor
     float4* p = reinterpret_cast<float4*>(out + ((int64_t)b * Cout + c) * plane);
     const int64_t n4 = plane >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -774,7 +782,9 @@ cudaError_t mic_launch(const FoaArgs& a, const PlanDev& pd, int* maxkey, float t
     const size_t smem = mic_smem_bytes(pd);
     cudaError_t e = from_spectra ? mic_set_attr<2>() : mic_set_attr<0>();
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(maxkey, 0x80, (size_t)a.B * 4 * sizeof(int), st);  // key 0x80808080: below any dB value
+    e = cudaMemsetAsync(maxkey, 0x80, (size_t)a.B * 4 * sizeof(int), st);  // maxima: key 0x80808080, below any dB value
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(maxkey + (size_t)a.B * 4, 0x7f, (size_t)a.B * 4 * sizeof(int), st);   // minima: key 0x7f7f7f7f, above any
     if (e != cudaSuccess) return e;
     int gx = sm_count < a.n_tiles ? sm_count : a.n_tiles;
     if (from_spectra) {
