@@ -113,7 +113,12 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
     float* win_s = tw_s + 32 * kTwStride;                                  // [lane][kWinStride]: window[32*m + lane] * 0.5, m = 0..31
     float* wab_s = win_s + 32 * kWinStride;                                // 32 * kWabStride          (item form: iw, iP * 32 float2)
     int* gseg_s = reinterpret_cast<int*>(wab_s + (kItem ? 64 * pd.iP : 32 * kWabStride));   // gseg_pad (item form: none)
+#ifdef SELD_TMEM_TABLES
+    // item form with the tables in tensor memory: shared memory holds the per-warp regions only (what is left of the 228 KB is L1)
+    float* R_all = kItem ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(gseg_s + pd.gseg_pad);   // W * region
+#else
     float* R_all = reinterpret_cast<float*>(gseg_s + (kItem ? 0 : pd.gseg_pad));            // W * region
+#endif
     constexpr int region = kItem ? kItemRegion : kRegion;                  // floats per warp (the exchange buffer aliases it)
     int* marked_s = reinterpret_cast<int*>(R_all + W * region);            // main form: some warp of this block marked a frame
 
@@ -157,6 +162,12 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
             return marked;
         }
     };
+#ifdef SELD_TMEM_TABLES
+    constexpr bool kSmemTables = !kItem;
+#else
+    constexpr bool kSmemTables = true;
+#endif
+    if constexpr (kSmemTables)
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
         const float2 w = pd.tw[brev5(r) * 32 + l];
@@ -164,7 +175,8 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         win_s[l * kWinStride + r] = pd.win[i] * in_scale;                   // int16 PCM: the 2^-15 of soundfile's conversion, exact
     }
     if constexpr (kItem) {
-        for (int i = tid; i < 64 * pd.iP; i += W * 32) wab_s[i] = reinterpret_cast<const float*>(pd.iw)[i];
+        if constexpr (kSmemTables)
+            for (int i = tid; i < 64 * pd.iP; i += W * 32) wab_s[i] = reinterpret_cast<const float*>(pd.iw)[i];
         for (int i = tid; i < W * region; i += W * 32) R_all[i] = 0.0f;     // the entries behind bin 512 are read with zero weights: keep them finite
     } else {
         for (int i = tid; i < 32 * kWabStride; i += W * 32) wab_s[i] = pd.wab[i];
@@ -610,7 +622,6 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
         if constexpr (kItem) {
             uint32_t wv[32];
             tmem_ld32(tmem_w, wv);
-            tmem_wait_ld(wv);
             static_for<0, 32>([&](auto mi) {
                 constexpr int m = decltype(mi)::value;
                 re[m] = vmuls(re[m], __uint_as_float(wv[m]));
@@ -643,7 +654,6 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 constexpr int h = decltype(hi)::value;
                 uint32_t tv[32];
                 tmem_ld32(tmem_w + 32 + 32 * h, tv);
-                tmem_wait_ld(tv);
                 static_for<0, 8>([&](auto qi) {
                     constexpr int p2 = 8 * h + decltype(qi)::value;         // positions 2*p2, 2*p2+1
                     constexpr int o = 4 * decltype(qi)::value;
@@ -801,7 +811,6 @@ foa_iv2_kernel(const FoaArgs a, const PlanDev pd) {
                 // touched until the wait, and tying them to the wait costs copies and spills.)
                 uint32_t w8[8];
                 tmem_ld8(tmem_w + 96 + 2 * (pd.ioff[c] + j0), w8);
-                tmem_wait_ld(w8);
 #endif
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj, ++zp, wp += 32) {
@@ -1069,7 +1078,12 @@ bool foa_iv2_supported(const PlanDev& pd, size_t smem_optin) {
 int foa_iv2_frames_per_tile() { return iv2_warps(); }
 
 static size_t iv2_item_smem_bytes(const PlanDev& pd, int W) {
+#ifdef SELD_TMEM_TABLES
+    (void)pd;
+    return (size_t)(W * kItemRegion + 4) * sizeof(float);                   // the tables live in tensor memory
+#else
     return (size_t)(32 * kTwStride + 32 * kWinStride + 64 * pd.iP + W * kItemRegion + 4) * sizeof(float);
+#endif
 }
 
 template <int W, typename TIn, bool kIV, bool kItem = false>

@@ -32,7 +32,7 @@
 // the 64 twiddle floats of the lane, (cos, cos', -sin, -sin') per pair of positions: from tensor memory (two loads, then
 // compile-time indexing) or from the shared-memory table
 #ifdef SELD_TMEM_TABLES
-#define TW_FETCH() uint32_t tvA[32], tvB[32]; tmem_ld32(tmem_w + 32, tvA); tmem_ld32(tmem_w + 64, tvB); tmem_wait_ld(tvA); tmem_wait_ld(tvB)
+#define TW_FETCH() uint32_t tvA[32], tvB[32]; tmem_ld32(tmem_w + 32, tvA); tmem_ld32(tmem_w + 64, tvB);
 #define TW4(p2) make_float4(__uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7)]), __uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7) + 1]), \
                             __uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7) + 2]), __uint_as_float(((p2) < 8 ? tvA : tvB)[4 * ((p2) & 7) + 3]))
 #else
@@ -101,17 +101,25 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     float* tw_s = reinterpret_cast<float*>(smem_raw);                      // [lane][kTwStride]: W1024^(lane*brev5(p)) as (cos_p, cos_p+1, -sin_p, -sin_p+1), p even
     float* win_s = tw_s + 32 * kTwStride;                                  // [lane][kWinStride]: window[32*m + lane] * 0.5
     float* wab_s = win_s + 32 * kWinStride;                                // item form of the mel bank: iw, iP * 32 float2 (a, b)
+#ifdef SELD_TMEM_TABLES
+    float* R_all = reinterpret_cast<float*>(smem_raw);                     // tables in tensor memory: shared memory holds the per-warp regions only
+    constexpr bool kSmemTables = false;
+#else
     float* R_all = wab_s + 64 * pd.iP;                                     // W * kRegion
+    constexpr bool kSmemTables = true;
+#endif
     int* marked_s = reinterpret_cast<int*>(R_all + W * kRegion);           // main form: some warp of this block marked a frame
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if constexpr (kSmemTables)
     for (int i = tid; i < 1024; i += W * 32) {
         const int l = i & 31, r = i >> 5;                                  // pd.tw is [ka][lane], pd.win is [32*m + lane]
         const float2 w = pd.tw[brev5(r) * 32 + l];                         // positions (2j, 2j+1) share one float4: (cos, cos', -sin, -sin')
         tw_s[l * kTwStride + 4 * (r >> 1) + (r & 1)] = w.x; tw_s[l * kTwStride + 4 * (r >> 1) + 2 + (r & 1)] = w.y;
         win_s[l * kWinStride + r] = pd.win[i];
     }
-    for (int i = tid; i < 64 * pd.iP; i += W * 32) wab_s[i] = reinterpret_cast<const float*>(pd.iw)[i];
+    if constexpr (kSmemTables)
+        for (int i = tid; i < 64 * pd.iP; i += W * 32) wab_s[i] = reinterpret_cast<const float*>(pd.iw)[i];
     if (tid == 0) *marked_s = 0;
     // the lane-private tables also go to tensor memory (tmem_tables.cuh): window [0, 32), twiddles in this kernel's layout
     // [32, 96), mel weights [96, 96 + 2 iP); the loop reads them from there, off the shared-memory pipe
@@ -275,7 +283,6 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         {
             uint32_t wv[32];
             tmem_ld32(tmem_w, wv);
-            tmem_wait_ld(wv);
             static_for<0, 32>([&](auto mi) {
                 constexpr int m = decltype(mi)::value;
                 re[m] = vmuls(re[m], __uint_as_float(wv[m]));
@@ -436,7 +443,6 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
 #ifdef SELD_TMEM_TABLES
                     uint32_t w8[8];
                     tmem_ld8(tmem_w + 96 + 2 * (pd.ioff[c] + j0), w8);
-                    tmem_wait_ld(w8);
 #endif
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj, ++qp, wp += 32) {
@@ -729,7 +735,12 @@ __global__ void mic_topdb_kernel(float* __restrict__ out, const int* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 static size_t mic_smem_bytes(const PlanDev& pd) {
+#ifdef SELD_TMEM_TABLES
+    (void)pd;
+    return (size_t)(mic::kW * mic::kRegion + 4) * sizeof(float);           // the tables live in tensor memory
+#else
     return (size_t)(32 * mic::kTwStride + 32 * mic::kWinStride + 64 * pd.iP + mic::kW * mic::kRegion + 4) * sizeof(float);
+#endif
 }
 
 bool mic_supported(const PlanDev& pd, size_t smem_optin) {
