@@ -16,7 +16,9 @@
 //      builds Z[l + 32m] for all m from the shared unit phasors X_c/|X_c| (bins above 512 are the
 //      conjugates of 1024-k), runs the 32-point inverse stage in registers, twiddles, exchanges, and -- because
 //      only lags [-32, 32) are kept -- evaluates just the two needed outputs of the second stage.
-//      Pass 0 does two transforms in the two float2 halves; pass 1 the third as one internally packed
+//      Pass 0 does two transforms in the two float2 halves (pairs 01 + i 12 | 03 + i 23: with the phasors kept as
+//      the pairs (u0, u2), (u1, u3) of the untangle step those four products are packed operations) and leaves
+//      the products of pairs 02 and 13 where the phasors were; pass 1 transforms those as one internally packed
 //      transform (fft32_dit) with scalar exchange planes.
 // A second, element-wise kernel applies the top_db floor once every frame's maximum is known.
 #include <cuda_runtime.h>
@@ -386,8 +388,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                     const float2 n02 = make_float2(inv_mag(p02.x), inv_mag(p02.y));
                     min_n = fminf(min_n, fminf(n02.x, n02.y));
                     const float2 ur = __fmul2_rn(ar, n02), ui = __fmul2_rn(ai, n02);
-                    spec[pass * kSpecStride + k] = make_float2(ur.x, ui.x);
-                    spec[(pass + 2) * kSpecStride + k] = make_float2(ur.y, ui.y);
+                    spec[(2 * pass) * kSpecStride + k] = ur;               // pass 0: (u0, u2), pass 1: (u1, u3), real and imaginary parts
+                    spec[(2 * pass + 1) * kSpecStride + k] = ui;
                     if (pass == 1) {                                        // pair rows (P0, P2), (P1, P3) in natural bin order
                         reinterpret_cast<float2*>(R)[k] = keep02[kb];
                         reinterpret_cast<float2*>(R)[kItemRow + k] = p02;
@@ -411,10 +413,10 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 if (__float_as_uint(ur02.x + ui02.x + ur13.x + ui13.x + ur02.y + ui02.y + ur13.y + ui13.y) == 0x12345678u)
 #endif
                 {
-                spec[0 * kSpecStride + k] = make_float2(ur02.x, ui02.x);
-                spec[1 * kSpecStride + k] = make_float2(ur13.x, ui13.x);
-                spec[2 * kSpecStride + k] = make_float2(ur02.y, ui02.y);
-                spec[3 * kSpecStride + k] = make_float2(ur13.y, ui13.y);
+                spec[0 * kSpecStride + k] = ur02;                           // pairs as they come out of the untangle step:
+                spec[1 * kSpecStride + k] = ui02;                           // (Re u0, Re u2), (Im u0, Im u2), (Re u1, Re u3), (Im u1, Im u3)
+                spec[2 * kSpecStride + k] = ur13;
+                spec[3 * kSpecStride + k] = ui13;
                 }
                 reinterpret_cast<float2*>(R)[k] = p02;                      // pair rows (P0, P2), (P1, P3) in natural bin order
                 reinterpret_cast<float2*>(R)[kItemRow + k] = p13;
@@ -540,31 +542,59 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         // pass 0 = pairs (01, 02 | 03, 12) as two transforms packed in float2 halves, pass 1 = pairs (13, 23) as
         // one transform packed internally (fft32_dit).
         constexpr float kInvN = 1.0f / 1024.0f;
-        // unit phasor of channel c at bin k = lane + 32 m (bins above 512 are conj(u[1024 - k]))
-        auto load_u = [&](int c, int kk, float sg) {
-            float2 u = spec[c * kSpecStride + kk];
-            u.y *= sg;
-            return u;
-        };
         // angle(0) = 0: a vanishing cross-spectrum bin must contribute the phasor 1.  That needs two compares and a
         // select per product; frames without any vanishing bin (all but digital silence / dead channels) skip them.
         const bool any_zero = __any_sync(0xffffffffu, min_n == 0.0f);
 #ifndef MABL_NOGCC0
         {
+            // phasors kept as the pairs (u0, u2) and (u1, u3): conj(u0) (u1, u3) and conj(u2) (u1, u3) are four packed operations
+            // each and give the pairs 01, 03, 21, 23; transforms: x halves Z = P01 + i P12 (P12 = conj(P21)), y halves Z = P03 + i P23.
+            // The two products left, P02 and P13, are taken here as well, from the same four loads, for the bins a lane owns
+            // (k <= 512), and written over the phasors of those bins (rows 0 and 1: the mirrored reads of all lanes come first),
+            // so pass 1 loads two values per input and multiplies nothing.
             auto build = [&](auto check_c) {
                 constexpr bool kCheck = decltype(check_c)::value;
-                static_for<0, 32>([&](auto mi) {
+                auto one = [&](auto mi) {
                     constexpr int m = decltype(mi)::value;
                     const int k = lane + 32 * m;
                     const bool up = k > 512;
                     const int kk = up ? 1024 - k : k;
                     const float sg = up ? -1.0f : 1.0f;
-                    const float2 u0 = load_u(0, kk, sg), u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
-                    const float2 a1 = cross_phasor<kCheck>(u0, u1), b1 = cross_phasor<kCheck>(u0, u2);
-                    const float2 a2 = cross_phasor<kCheck>(u0, u3), b2 = cross_phasor<kCheck>(u1, u2);
-                    re[m] = make_float2(a1.x - b1.y, a2.x - b2.y);
-                    im[m] = make_float2(a1.y + b1.x, a2.y + b2.x);
-                });
+                    // bins above 512 are the conjugates of bins 1024 - k: with every phasor conjugated every product is, too
+                    // (m = 16 is the one row where that depends on the lane)
+                    const float2 r02 = spec[0 * kSpecStride + kk], r13 = spec[2 * kSpecStride + kk];
+                    float2 i02 = spec[1 * kSpecStride + kk], i13 = spec[3 * kSpecStride + kk];
+                    if constexpr (m == 16) { i02 = vmuls(i02, sg); i13 = vmuls(i13, sg); }
+                    float2 Ar = vfmas(i13, i02.x, vmuls(r13, r02.x));         // Re (P01, P03)
+                    float2 Ai = vfmas(r13, -i02.x, vmuls(i13, r02.x));        // Im (P01, P03)
+                    float2 Br = vfmas(i13, i02.y, vmuls(r13, r02.y));         // Re (P21, P23)
+                    float2 Bi = vfmas(r13, -i02.y, vmuls(i13, r02.y));        // Im (P21, P23)
+                    if constexpr (kCheck) {
+                        if (Ar.x == 0.0f && Ai.x == 0.0f) Ar.x = 1.0f;
+                        if (Ar.y == 0.0f && Ai.y == 0.0f) Ar.y = 1.0f;
+                        if (Br.x == 0.0f && Bi.x == 0.0f) Br.x = 1.0f;
+                        if (Br.y == 0.0f && Bi.y == 0.0f) Br.y = 1.0f;
+                    }
+                    if constexpr (m > 16) {
+                        re[m] = __ffma2_rn(Bi, make_float2(-1.0f, 1.0f), Ar);
+                        im[m] = vsub(Br, Ai);
+                    } else {
+                        re[m] = __ffma2_rn(Bi, make_float2(1.0f, -1.0f), Ar); // Re P01 - Im P12 | Re P03 - Im P23
+                        im[m] = vadd(Ai, Br);                                 // Im P01 + Re P12 | Im P03 + Re P23
+                    }
+                    if constexpr (m <= 16) {
+                        if (m < 16 || lane == 0) {
+                            const float2 p02 = cross_phasor<kCheck>(make_float2(r02.x, i02.x), make_float2(r02.y, i02.y));
+                            const float2 p13 = cross_phasor<kCheck>(make_float2(r13.x, i13.x), make_float2(r13.y, i13.y));
+                            spec[0 * kSpecStride + k] = p02;
+                            spec[1 * kSpecStride + k] = p13;
+                        }
+                    }
+                };
+                static_for<16, 32>(one);                                      // mirrored reads (m = 16: lane 0 owns bin 512, which nobody else reads)
+                __syncwarp();                                                 // every mirrored read is done: a lane's own bins may be overwritten
+                static_for<0, 16>(one);
+                __syncwarp();
             };
             if (any_zero) build(std::true_type{}); else build(std::false_type{});
             // inverse 32-point stage over m: swap(FFT(swap(z)))
@@ -611,18 +641,17 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             });
             // real part = first pair of a transform, imaginary part = second pair
             float* g = ob + (int64_t)4 * ch_stride;
-            g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;
-            g[1 * ch_stride + lane] = c31i.x * kInvN;  g[1 * ch_stride + 32 + lane] = c0i.x * kInvN;
-            g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;
-            g[3 * ch_stride + lane] = c31i.y * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.y * kInvN;
+            g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;   // pair 01
+            g[3 * ch_stride + lane] = c31i.x * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.x * kInvN;   // pair 12
+            g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;   // pair 03
+            g[5 * ch_stride + lane] = c31i.y * kInvN;  g[5 * ch_stride + 32 + lane] = c0i.y * kInvN;   // pair 23
         }
 #endif
 #ifndef MABL_NOGCC1
         {
             // one transform: position p of (zr, zi) holds the input pair (z[m = 2p], z[m = 2p + 1])
             float2 zr[16], zi[16];
-            auto build = [&](auto check_c) {
-                constexpr bool kCheck = decltype(check_c)::value;
+            {
                 static_for<0, 16>([&](auto pi) {
                     constexpr int p = decltype(pi)::value;
                     float rr[2], ii[2];
@@ -631,15 +660,13 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                         const int k = lane + 32 * (2 * p + e);
                         const bool up = k > 512;
                         const int kk = up ? 1024 - k : k;
-                        const float sg = up ? -1.0f : 1.0f;
-                        const float2 u1 = load_u(1, kk, sg), u2 = load_u(2, kk, sg), u3 = load_u(3, kk, sg);
-                        const float2 a = cross_phasor<kCheck>(u1, u3), b = cross_phasor<kCheck>(u2, u3);
-                        rr[e] = a.x - b.y; ii[e] = a.y + b.x;
+                        const float2 a = spec[0 * kSpecStride + kk], b = spec[1 * kSpecStride + kk];   // P02, P13 (pass 0 left them there)
+                        rr[e] = up ? a.x + b.y : a.x - b.y;                 // Z = P02 + i P13, conjugated products above bin 512
+                        ii[e] = up ? b.x - a.y : b.x + a.y;
                     }
                     zr[p] = make_float2(rr[0], rr[1]); zi[p] = make_float2(ii[0], ii[1]);
                 });
-            };
-            if (any_zero) build(std::true_type{}); else build(std::false_type{});
+            }
             fft32_dit(zi, zr);                                              // position q': (A[lane][q], A[lane][q + 16]), q = brev4(q')
             float* fr = R;                                                  // two planes of 32 x 34 floats in the exchange area
             float* fi = R + 32 * kXStride;
@@ -678,9 +705,9 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                 a31i = __ffma2_rn(pr, make_float2(-s0, -s1), __ffma2_rn(pi, make_float2(c0, c1), a31i));
             });
             __syncwarp();                                                   // the next frame reuses the exchange area
-            float* g = ob + (int64_t)8 * ch_stride;
+            float* g = ob + (int64_t)5 * ch_stride;                         // pairs 02 and 13: planes 5 and 8
             g[0 * ch_stride + lane] = (a31r.x + a31r.y) * kInvN;  g[0 * ch_stride + 32 + lane] = (a0r.x + a0r.y) * kInvN;
-            g[1 * ch_stride + lane] = (a31i.x + a31i.y) * kInvN;  g[1 * ch_stride + 32 + lane] = (a0i.x + a0i.y) * kInvN;
+            g[3 * ch_stride + lane] = (a31i.x + a31i.y) * kInvN;  g[3 * ch_stride + 32 + lane] = (a0i.x + a0i.y) * kInvN;
         }
 #endif
     }
