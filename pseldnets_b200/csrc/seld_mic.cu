@@ -205,6 +205,7 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
     const int nblk = kRedo ? a.redo_grid : (int)gridDim.x;
     const int tile_lo = (int)(((int64_t)blockIdx.x * a.n_tiles) / nblk), tile_hi = (int)(((int64_t)(blockIdx.x + 1) * a.n_tiles) / nblk);
     int tile = tile_lo - 1;
+    int tb = tile_lo / a.tiles_per_clip, tr = tile_lo - tb * a.tiles_per_clip - 1;   // (clip, tile within the clip), advanced without a division per frame
     // redo form: item j = (tile number j / W of that block, warp slot j % W)
     const int redo_tiles = kRedo ? tile_hi - tile_lo : 0;
     const int redo_items = redo_tiles * W;
@@ -221,8 +222,9 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         if constexpr (!kRedo) {
             ++tile;
             if (tile >= tile_hi) break;
-            b = tile / a.tiles_per_clip;
-            t = (tile - b * a.tiles_per_clip) * W + warp;
+            if (++tr >= a.tiles_per_clip) { tr = 0; ++tb; }
+            b = tb;
+            t = tr * W + warp;
             if (t >= a.T) continue;
         } else {
             while (todo == 0u) {
