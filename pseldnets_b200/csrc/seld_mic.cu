@@ -552,8 +552,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             // phasors kept as the pairs (u0, u2) and (u1, u3): conj(u0) (u1, u3) and conj(u2) (u1, u3) are four packed operations
             // each and give the pairs 01, 03, 21, 23; transforms: x halves Z = P01 + i P12 (P12 = conj(P21)), y halves Z = P03 + i P23.
             // The two products left, P02 and P13, are taken here as well, from the same four loads, for the bins a lane owns
-            // (k <= 512), and written over the phasors of those bins (rows 0 and 1: the mirrored reads of all lanes come first),
-            // so pass 1 loads two values per input and multiplies nothing.
+            // (k <= 512), and written, already combined into pass 1's input, over the phasors of those bins (rows 0 and 1: the
+            // mirrored reads of all lanes come first), so pass 1 loads one value per input and computes nothing.
             auto build = [&](auto check_c) {
                 constexpr bool kCheck = decltype(check_c)::value;
                 auto one = [&](auto mi) {
@@ -588,8 +588,10 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                         if (m < 16 || lane == 0) {
                             const float2 p02 = cross_phasor<kCheck>(make_float2(r02.x, i02.x), make_float2(r02.y, i02.y));
                             const float2 p13 = cross_phasor<kCheck>(make_float2(r13.x, i13.x), make_float2(r13.y, i13.y));
-                            spec[0 * kSpecStride + k] = p02;
-                            spec[1 * kSpecStride + k] = p13;
+                            // pass 1 transforms Z = P02 + i P13: row 0 takes Z[k] itself, row 1 what the reader of the mirrored
+                            // bin needs, conj(P02) + i conj(P13) = Z[1024 - k]: one load per input there
+                            spec[0 * kSpecStride + k] = make_float2(p02.x - p13.y, p02.y + p13.x);
+                            spec[1 * kSpecStride + k] = make_float2(p02.x + p13.y, p13.x - p02.y);
                         }
                     }
                 };
@@ -633,14 +635,18 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
             // second stage, only n1 = 0 (lag n2 = lane) and n1 = 31 (lag lane - 32):
             //   c0 = sum_k1 A'[k1],  c31 = sum_k1 A'[k1] * (cos(2 pi k1/32) - i sin(2 pi k1/32))
             float2 c0r = re[0], c0i = im[0], c31r = re[0], c31i = im[0];
-            static_for<1, 32>([&](auto ki) {
+            // terms k1 and 32 - k1 share the cosine and have opposite sines: sums and differences first
+            static_for<1, 16>([&](auto ki) {
                 constexpr int k1 = decltype(ki)::value;
-                constexpr float c = (float)(k1 <= 16 ? cos32(k1) : cos32(32 - k1));
-                constexpr float sn = (float)(k1 <= 16 ? sin32(k1) : -sin32(32 - k1));
-                c0r = vadd(c0r, re[k1]); c0i = vadd(c0i, im[k1]);
-                c31r = vfmas(im[k1], sn, vfmas(re[k1], c, c31r));           // Re += r c + i s
-                c31i = vfmas(re[k1], -sn, vfmas(im[k1], c, c31i));          // Im += i c - r s
+                constexpr float c = (float)cos32(k1), sn = (float)sin32(k1);
+                const float2 sr = vadd(re[k1], re[32 - k1]), si = vadd(im[k1], im[32 - k1]);
+                const float2 dr = vsub(re[k1], re[32 - k1]), di = vsub(im[k1], im[32 - k1]);
+                c0r = vadd(c0r, sr); c0i = vadd(c0i, si);
+                c31r = vfmas(di, sn, vfmas(sr, c, c31r));
+                c31i = vfmas(dr, -sn, vfmas(si, c, c31i));
             });
+            c0r = vadd(c0r, re[16]); c0i = vadd(c0i, im[16]);
+            c31r = vsub(c31r, re[16]); c31i = vsub(c31i, im[16]);
             // real part = first pair of a transform, imaginary part = second pair
             float* g = ob + (int64_t)4 * ch_stride;
             g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;   // pair 01
@@ -662,9 +668,8 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
                         const int k = lane + 32 * (2 * p + e);
                         const bool up = k > 512;
                         const int kk = up ? 1024 - k : k;
-                        const float2 a = spec[0 * kSpecStride + kk], b = spec[1 * kSpecStride + kk];   // P02, P13 (pass 0 left them there)
-                        rr[e] = up ? a.x + b.y : a.x - b.y;                 // Z = P02 + i P13, conjugated products above bin 512
-                        ii[e] = up ? b.x - a.y : b.x + a.y;
+                        const float2 z = spec[(up ? 1 : 0) * kSpecStride + kk];   // Z = P02 + i P13 as pass 0 left it (row 1: for the mirrored bin)
+                        rr[e] = z.x; ii[e] = z.y;
                     }
                     zr[p] = make_float2(rr[0], rr[1]); zi[p] = make_float2(ii[0], ii[1]);
                 });
