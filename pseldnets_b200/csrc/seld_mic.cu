@@ -20,6 +20,8 @@
 //      the pairs (u0, u2), (u1, u3) of the untangle step those four products are packed operations) and leaves
 //      the products of pairs 02 and 13 where the phasors were; pass 1 transforms those as one internally packed
 //      transform (fft32_dit) with scalar exchange planes.
+// Order in the kernel: 1, 2, 4, 3 -- the GCC passes exchange through phasor rows 2 and 3 (free once pass 0 has its input), so the
+// power rows of step 3 stay in the exchange area of step 1 until the mel step reads them (measured -1.2 % against mel first).
 // A second, element-wise kernel applies the top_db floor once every frame's maximum is known.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,8 +49,8 @@ namespace mic {
 using namespace melseg;
 
 constexpr int kW = 8;                      // warps (frames) per block
-constexpr int kSpecStride = 528;           // float2 per channel spectrum: 513 + pad to a whole number of 128-byte lines (with 516 the
-                                           // 256-byte warp accesses of channels 1-3 straddled three lines instead of two)
+constexpr int kSpecStride = 544;           // float2 per phasor row: 513 + pad to a whole number of 128-byte lines (with 516 the 256-byte warp
+                                           // accesses of rows 1-3 straddled three lines instead of two); two rows hold a 32 x 34 exchange buffer
 constexpr int kSpec = 4 * kSpecStride * 2; // floats: four spectra
 constexpr int kXStride = 34;                // exchange buffer row stride in float2 (even: 128-bit reads)
 constexpr int kRowsArea = 32 * kXStride * 2; // floats: 32x34 float2 exchange buffer; the 4 power rows (2112) alias it
@@ -57,6 +59,7 @@ constexpr int kWinStride = 36;              // lane-major window table row: 32 f
 constexpr int kItemRow = 544;               // float2 per power pair-row in natural bin order: (P0, P2) and (P1, P3) fill the exchange area exactly
 constexpr int kItemSlots = 136, kItemZero = 128;   // piece sums: 4 arrays of kItemSlots float2 (4 classes x 32 lanes, the slot kept at zero, pad)
 static_assert(2 * 2 * kItemRow <= kRowsArea && 4 * 2 * kItemSlots <= kRowsArea, "rows and piece sums live in the exchange area");
+static_assert(2 * kSpecStride * 2 >= kRowsArea, "the GCC passes exchange through phasor rows 2 and 3");
 constexpr int kRegion = kSpec + kRowsArea;
 static_assert(kRegion % 32 == 0 && kSpec % 32 == 0 && (kSpecStride * 2) % 32 == 0, "per-warp regions and their parts start on 128-byte lines");
 // imbalance rule as in seld_foa_iv2.cu: a loose ratio that three of eight neighbouring bands must cross, a strict one
@@ -428,8 +431,188 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         }  // pass
         if constexpr (kMode == 1) continue;
 
-        // ---------------- log-mel of the four power rows (unclamped dB + running maximum)
         float* ob = a.out + (((int64_t)b * a.Cout) * a.T + t) * M;
+        // (the GCC passes come before the mel step: they exchange through phasor rows 2 and 3, the power rows stay where they are)
+        // ---------------- GCC-PHAT.  Two real correlations per complex inverse transform (Z = ph_a + i ph_b):
+        // pass 0 = pairs (01, 02 | 03, 12) as two transforms packed in float2 halves, pass 1 = pairs (13, 23) as
+        // one transform packed internally (fft32_dit).
+        constexpr float kInvN = 1.0f / 1024.0f;
+        float2* const xg = spec + 2 * kSpecStride;                          // exchange buffer of both passes: phasor rows 2 and 3, free once pass 0 has its input
+        // angle(0) = 0: a vanishing cross-spectrum bin must contribute the phasor 1.  That needs two compares and a
+        // select per product; frames without any vanishing bin (all but digital silence / dead channels) skip them.
+        const bool any_zero = __any_sync(0xffffffffu, min_n == 0.0f);
+#ifndef MABL_NOGCC0
+        {
+            // phasors kept as the pairs (u0, u2) and (u1, u3): conj(u0) (u1, u3) and conj(u2) (u1, u3) are four packed operations
+            // each and give the pairs 01, 03, 21, 23; transforms: x halves Z = P01 + i P12 (P12 = conj(P21)), y halves Z = P03 + i P23.
+            // The two products left, P02 and P13, are taken here as well, from the same four loads, for the bins a lane owns
+            // (k <= 512), and written, already combined into pass 1's input, over the phasors of those bins (rows 0 and 1: the
+            // mirrored reads of all lanes come first), so pass 1 loads one value per input and computes nothing.
+            auto build = [&](auto check_c) {
+                constexpr bool kCheck = decltype(check_c)::value;
+                auto one = [&](auto mi) {
+                    constexpr int m = decltype(mi)::value;
+                    const int k = lane + 32 * m;
+                    const bool up = k > 512;
+                    const int kk = up ? 1024 - k : k;
+                    const float sg = up ? -1.0f : 1.0f;
+                    // bins above 512 are the conjugates of bins 1024 - k: with every phasor conjugated every product is, too
+                    // (m = 16 is the one row where that depends on the lane)
+                    const float2 r02 = spec[0 * kSpecStride + kk], r13 = spec[2 * kSpecStride + kk];
+                    float2 i02 = spec[1 * kSpecStride + kk], i13 = spec[3 * kSpecStride + kk];
+                    if constexpr (m == 16) { i02 = vmuls(i02, sg); i13 = vmuls(i13, sg); }
+                    float2 Ar = vfmas(i13, i02.x, vmuls(r13, r02.x));         // Re (P01, P03)
+                    float2 Ai = vfmas(r13, -i02.x, vmuls(i13, r02.x));        // Im (P01, P03)
+                    float2 Br = vfmas(i13, i02.y, vmuls(r13, r02.y));         // Re (P21, P23)
+                    float2 Bi = vfmas(r13, -i02.y, vmuls(i13, r02.y));        // Im (P21, P23)
+                    if constexpr (kCheck) {
+                        if (Ar.x == 0.0f && Ai.x == 0.0f) Ar.x = 1.0f;
+                        if (Ar.y == 0.0f && Ai.y == 0.0f) Ar.y = 1.0f;
+                        if (Br.x == 0.0f && Bi.x == 0.0f) Br.x = 1.0f;
+                        if (Br.y == 0.0f && Bi.y == 0.0f) Br.y = 1.0f;
+                    }
+                    if constexpr (m > 16) {
+                        re[m] = __ffma2_rn(Bi, make_float2(-1.0f, 1.0f), Ar);
+                        im[m] = vsub(Br, Ai);
+                    } else {
+                        re[m] = __ffma2_rn(Bi, make_float2(1.0f, -1.0f), Ar); // Re P01 - Im P12 | Re P03 - Im P23
+                        im[m] = vadd(Ai, Br);                                 // Im P01 + Re P12 | Im P03 + Re P23
+                    }
+                    if constexpr (m <= 16) {
+                        if (m < 16 || lane == 0) {
+                            const float2 p02 = cross_phasor<kCheck>(make_float2(r02.x, i02.x), make_float2(r02.y, i02.y));
+                            const float2 p13 = cross_phasor<kCheck>(make_float2(r13.x, i13.x), make_float2(r13.y, i13.y));
+                            // pass 1 transforms Z = P02 + i P13: row 0 takes Z[k] itself, row 1 what the reader of the mirrored
+                            // bin needs, conj(P02) + i conj(P13) = Z[1024 - k]: one load per input there
+                            spec[0 * kSpecStride + k] = make_float2(p02.x - p13.y, p02.y + p13.x);
+                            spec[1 * kSpecStride + k] = make_float2(p02.x + p13.y, p13.x - p02.y);
+                        }
+                    }
+                };
+                static_for<16, 32>(one);                                      // mirrored reads (m = 16: lane 0 owns bin 512, which nobody else reads)
+                __syncwarp();                                                 // every mirrored read is done: a lane's own bins may be overwritten
+                static_for<0, 16>(one);
+                __syncwarp();
+            };
+            if (any_zero) build(std::true_type{}); else build(std::false_type{});
+            // inverse 32-point stage over m: swap(FFT(swap(z)))
+            fft32(im, re);                                                  // position p: A[lane][n2 = brev5(p)]
+            TW_FETCH();
+            static_for<0, 16>([&](auto pi) {                                // table holds (cos, -sin): multiply by (cos + i sin)
+                constexpr int p2 = decltype(pi)::value;
+                const float4 w4 = TW4(p2);
+                if constexpr (p2 > 0) {
+                    const float2 r = re[2 * p2], i = im[2 * p2];
+                    re[2 * p2] = vfmas(i, w4.z, vmuls(r, w4.x));
+                    im[2 * p2] = vfmas(i, w4.x, vmuls(r, -w4.z));
+                }
+                const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
+                re[2 * p2 + 1] = vfmas(i, w4.w, vmuls(r, w4.y));
+                im[2 * p2 + 1] = vfmas(i, w4.y, vmuls(r, -w4.w));
+            });
+            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; xg[brev5(p) * kXStride + lane] = re[p]; });
+            __syncwarp();
+            static_for<0, 16>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const float4 v = *reinterpret_cast<const float4*>(xg + lane * kXStride + 2 * j);
+                re[2 * j] = make_float2(v.x, v.y); re[2 * j + 1] = make_float2(v.z, v.w);
+            });
+            __syncwarp();
+            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; xg[brev5(p) * kXStride + lane] = im[p]; });
+            __syncwarp();
+            static_for<0, 16>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const float4 v = *reinterpret_cast<const float4*>(xg + lane * kXStride + 2 * j);
+                im[2 * j] = make_float2(v.x, v.y); im[2 * j + 1] = make_float2(v.z, v.w);
+            });
+            __syncwarp();
+            // second stage, only n1 = 0 (lag n2 = lane) and n1 = 31 (lag lane - 32):
+            //   c0 = sum_k1 A'[k1],  c31 = sum_k1 A'[k1] * (cos(2 pi k1/32) - i sin(2 pi k1/32))
+            float2 c0r = re[0], c0i = im[0], c31r = re[0], c31i = im[0];
+            // terms k1 and 32 - k1 share the cosine and have opposite sines: sums and differences first
+            static_for<1, 16>([&](auto ki) {
+                constexpr int k1 = decltype(ki)::value;
+                constexpr float c = (float)cos32(k1), sn = (float)sin32(k1);
+                const float2 sr = vadd(re[k1], re[32 - k1]), si = vadd(im[k1], im[32 - k1]);
+                const float2 dr = vsub(re[k1], re[32 - k1]), di = vsub(im[k1], im[32 - k1]);
+                c0r = vadd(c0r, sr); c0i = vadd(c0i, si);
+                c31r = vfmas(di, sn, vfmas(sr, c, c31r));
+                c31i = vfmas(dr, -sn, vfmas(si, c, c31i));
+            });
+            c0r = vadd(c0r, re[16]); c0i = vadd(c0i, im[16]);
+            c31r = vsub(c31r, re[16]); c31i = vsub(c31i, im[16]);
+            // real part = first pair of a transform, imaginary part = second pair
+            float* g = ob + (int64_t)4 * ch_stride;
+            g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;   // pair 01
+            g[3 * ch_stride + lane] = c31i.x * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.x * kInvN;   // pair 12
+            g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;   // pair 03
+            g[5 * ch_stride + lane] = c31i.y * kInvN;  g[5 * ch_stride + 32 + lane] = c0i.y * kInvN;   // pair 23
+        }
+#endif
+#ifndef MABL_NOGCC1
+        {
+            // one transform: position p of (zr, zi) holds the input pair (z[m = 2p], z[m = 2p + 1])
+            float2 zr[16], zi[16];
+            {
+                static_for<0, 16>([&](auto pi) {
+                    constexpr int p = decltype(pi)::value;
+                    float rr[2], ii[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = lane + 32 * (2 * p + e);
+                        const bool up = k > 512;
+                        const int kk = up ? 1024 - k : k;
+                        const float2 z = spec[(up ? 1 : 0) * kSpecStride + kk];   // Z = P02 + i P13 as pass 0 left it (row 1: for the mirrored bin)
+                        rr[e] = z.x; ii[e] = z.y;
+                    }
+                    zr[p] = make_float2(rr[0], rr[1]); zi[p] = make_float2(ii[0], ii[1]);
+                });
+            }
+            fft32_dit(zi, zr);                                              // position q': (A[lane][q], A[lane][q + 16]), q = brev4(q')
+            float* fr = reinterpret_cast<float*>(xg);                       // two planes of 32 x 34 floats in the exchange area
+            float* fi = fr + 32 * kXStride;
+            TW_FETCH();
+            static_for<0, 16>([&](auto qi) {
+                constexpr int qp = decltype(qi)::value;
+                constexpr int q = brev4(qp);
+                // table positions brev5(q) (even) and brev5(q + 16) = brev5(q) + 1 share one float4: (cos, cos', -sin, -sin')
+                const float4 w4 = TW4(brev5(q) / 2);
+                float2 r = zr[qp], i = zi[qp];
+                if constexpr (q == 0) {                                     // W^0 = 1 for n2 = 0; n2 = 16 still needs its factor
+                    const float r1 = r.y, i1 = i.y;
+                    r.y = fmaf(i1, w4.w, r1 * w4.y);
+                    i.y = fmaf(i1, w4.y, r1 * -w4.w);
+                } else {
+                    const float2 C2 = make_float2(w4.x, w4.y), S2 = make_float2(w4.z, w4.w);
+                    const float2 t = __fmul2_rn(make_float2(-r.x, -r.y), S2);
+                    r = __ffma2_rn(i, S2, __fmul2_rn(r, C2));
+                    i = __ffma2_rn(i, C2, t);
+                }
+                fr[q * kXStride + lane] = r.x; fr[(q + 16) * kXStride + lane] = r.y;
+                fi[q * kXStride + lane] = i.x; fi[(q + 16) * kXStride + lane] = i.y;
+            });
+            __syncwarp();
+            // second stage for n1 = 0 and 31, two k1 terms per packed operation
+            float2 a0r = make_float2(0.f, 0.f), a0i = a0r, a31r = a0r, a31i = a0r;
+            static_for<0, 16>([&](auto ji) {
+                constexpr int j = decltype(ji)::value;
+                const float2 pr = *reinterpret_cast<const float2*>(fr + lane * kXStride + 2 * j);   // (A'[2j], A'[2j + 1])
+                const float2 pi = *reinterpret_cast<const float2*>(fi + lane * kXStride + 2 * j);
+                constexpr int k0 = 2 * j, k1 = 2 * j + 1;
+                constexpr float c0 = (float)(k0 <= 16 ? cos32(k0) : cos32(32 - k0)), c1 = (float)(k1 <= 16 ? cos32(k1) : cos32(32 - k1));
+                constexpr float s0 = (float)(k0 <= 16 ? sin32(k0) : -sin32(32 - k0)), s1 = (float)(k1 <= 16 ? sin32(k1) : -sin32(32 - k1));
+                a0r = __fadd2_rn(a0r, pr); a0i = __fadd2_rn(a0i, pi);
+                a31r = __ffma2_rn(pi, make_float2(s0, s1), __ffma2_rn(pr, make_float2(c0, c1), a31r));
+                a31i = __ffma2_rn(pr, make_float2(-s0, -s1), __ffma2_rn(pi, make_float2(c0, c1), a31i));
+            });
+            __syncwarp();                                                   // the next frame reuses the exchange area
+            float* g = ob + (int64_t)5 * ch_stride;                         // pairs 02 and 13: planes 5 and 8
+            g[0 * ch_stride + lane] = (a31r.x + a31r.y) * kInvN;  g[0 * ch_stride + 32 + lane] = (a0r.x + a0r.y) * kInvN;
+            g[3 * ch_stride + lane] = (a31i.x + a31i.y) * kInvN;  g[3 * ch_stride + 32 + lane] = (a0i.x + a0i.y) * kInvN;
+        }
+#endif
+
+        // ---------------- log-mel of the four power rows (unclamped dB + running maximum)
 #ifndef MABL_NOMEL
         {
             float2 aU[4][2], aV[4][2];                                      // piece sums per class, both pair rows
@@ -540,183 +723,6 @@ mic_features_kernel(const FoaArgs a, const PlanDev pd, int* __restrict__ maxkey)
         }
 #endif
 
-        // ---------------- GCC-PHAT.  Two real correlations per complex inverse transform (Z = ph_a + i ph_b):
-        // pass 0 = pairs (01, 02 | 03, 12) as two transforms packed in float2 halves, pass 1 = pairs (13, 23) as
-        // one transform packed internally (fft32_dit).
-        constexpr float kInvN = 1.0f / 1024.0f;
-        // angle(0) = 0: a vanishing cross-spectrum bin must contribute the phasor 1.  That needs two compares and a
-        // select per product; frames without any vanishing bin (all but digital silence / dead channels) skip them.
-        const bool any_zero = __any_sync(0xffffffffu, min_n == 0.0f);
-#ifndef MABL_NOGCC0
-        {
-            // phasors kept as the pairs (u0, u2) and (u1, u3): conj(u0) (u1, u3) and conj(u2) (u1, u3) are four packed operations
-            // each and give the pairs 01, 03, 21, 23; transforms: x halves Z = P01 + i P12 (P12 = conj(P21)), y halves Z = P03 + i P23.
-            // The two products left, P02 and P13, are taken here as well, from the same four loads, for the bins a lane owns
-            // (k <= 512), and written, already combined into pass 1's input, over the phasors of those bins (rows 0 and 1: the
-            // mirrored reads of all lanes come first), so pass 1 loads one value per input and computes nothing.
-            auto build = [&](auto check_c) {
-                constexpr bool kCheck = decltype(check_c)::value;
-                auto one = [&](auto mi) {
-                    constexpr int m = decltype(mi)::value;
-                    const int k = lane + 32 * m;
-                    const bool up = k > 512;
-                    const int kk = up ? 1024 - k : k;
-                    const float sg = up ? -1.0f : 1.0f;
-                    // bins above 512 are the conjugates of bins 1024 - k: with every phasor conjugated every product is, too
-                    // (m = 16 is the one row where that depends on the lane)
-                    const float2 r02 = spec[0 * kSpecStride + kk], r13 = spec[2 * kSpecStride + kk];
-                    float2 i02 = spec[1 * kSpecStride + kk], i13 = spec[3 * kSpecStride + kk];
-                    if constexpr (m == 16) { i02 = vmuls(i02, sg); i13 = vmuls(i13, sg); }
-                    float2 Ar = vfmas(i13, i02.x, vmuls(r13, r02.x));         // Re (P01, P03)
-                    float2 Ai = vfmas(r13, -i02.x, vmuls(i13, r02.x));        // Im (P01, P03)
-                    float2 Br = vfmas(i13, i02.y, vmuls(r13, r02.y));         // Re (P21, P23)
-                    float2 Bi = vfmas(r13, -i02.y, vmuls(i13, r02.y));        // Im (P21, P23)
-                    if constexpr (kCheck) {
-                        if (Ar.x == 0.0f && Ai.x == 0.0f) Ar.x = 1.0f;
-                        if (Ar.y == 0.0f && Ai.y == 0.0f) Ar.y = 1.0f;
-                        if (Br.x == 0.0f && Bi.x == 0.0f) Br.x = 1.0f;
-                        if (Br.y == 0.0f && Bi.y == 0.0f) Br.y = 1.0f;
-                    }
-                    if constexpr (m > 16) {
-                        re[m] = __ffma2_rn(Bi, make_float2(-1.0f, 1.0f), Ar);
-                        im[m] = vsub(Br, Ai);
-                    } else {
-                        re[m] = __ffma2_rn(Bi, make_float2(1.0f, -1.0f), Ar); // Re P01 - Im P12 | Re P03 - Im P23
-                        im[m] = vadd(Ai, Br);                                 // Im P01 + Re P12 | Im P03 + Re P23
-                    }
-                    if constexpr (m <= 16) {
-                        if (m < 16 || lane == 0) {
-                            const float2 p02 = cross_phasor<kCheck>(make_float2(r02.x, i02.x), make_float2(r02.y, i02.y));
-                            const float2 p13 = cross_phasor<kCheck>(make_float2(r13.x, i13.x), make_float2(r13.y, i13.y));
-                            // pass 1 transforms Z = P02 + i P13: row 0 takes Z[k] itself, row 1 what the reader of the mirrored
-                            // bin needs, conj(P02) + i conj(P13) = Z[1024 - k]: one load per input there
-                            spec[0 * kSpecStride + k] = make_float2(p02.x - p13.y, p02.y + p13.x);
-                            spec[1 * kSpecStride + k] = make_float2(p02.x + p13.y, p13.x - p02.y);
-                        }
-                    }
-                };
-                static_for<16, 32>(one);                                      // mirrored reads (m = 16: lane 0 owns bin 512, which nobody else reads)
-                __syncwarp();                                                 // every mirrored read is done: a lane's own bins may be overwritten
-                static_for<0, 16>(one);
-                __syncwarp();
-            };
-            if (any_zero) build(std::true_type{}); else build(std::false_type{});
-            // inverse 32-point stage over m: swap(FFT(swap(z)))
-            fft32(im, re);                                                  // position p: A[lane][n2 = brev5(p)]
-            TW_FETCH();
-            static_for<0, 16>([&](auto pi) {                                // table holds (cos, -sin): multiply by (cos + i sin)
-                constexpr int p2 = decltype(pi)::value;
-                const float4 w4 = TW4(p2);
-                if constexpr (p2 > 0) {
-                    const float2 r = re[2 * p2], i = im[2 * p2];
-                    re[2 * p2] = vfmas(i, w4.z, vmuls(r, w4.x));
-                    im[2 * p2] = vfmas(i, w4.x, vmuls(r, -w4.z));
-                }
-                const float2 r = re[2 * p2 + 1], i = im[2 * p2 + 1];
-                re[2 * p2 + 1] = vfmas(i, w4.w, vmuls(r, w4.y));
-                im[2 * p2 + 1] = vfmas(i, w4.y, vmuls(r, -w4.w));
-            });
-            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = re[p]; });
-            __syncwarp();
-            static_for<0, 16>([&](auto ji) {
-                constexpr int j = decltype(ji)::value;
-                const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
-                re[2 * j] = make_float2(v.x, v.y); re[2 * j + 1] = make_float2(v.z, v.w);
-            });
-            __syncwarp();
-            static_for<0, 32>([&](auto pi) { constexpr int p = decltype(pi)::value; scratch[brev5(p) * kXStride + lane] = im[p]; });
-            __syncwarp();
-            static_for<0, 16>([&](auto ji) {
-                constexpr int j = decltype(ji)::value;
-                const float4 v = *reinterpret_cast<const float4*>(scratch + lane * kXStride + 2 * j);
-                im[2 * j] = make_float2(v.x, v.y); im[2 * j + 1] = make_float2(v.z, v.w);
-            });
-            __syncwarp();
-            // second stage, only n1 = 0 (lag n2 = lane) and n1 = 31 (lag lane - 32):
-            //   c0 = sum_k1 A'[k1],  c31 = sum_k1 A'[k1] * (cos(2 pi k1/32) - i sin(2 pi k1/32))
-            float2 c0r = re[0], c0i = im[0], c31r = re[0], c31i = im[0];
-            // terms k1 and 32 - k1 share the cosine and have opposite sines: sums and differences first
-            static_for<1, 16>([&](auto ki) {
-                constexpr int k1 = decltype(ki)::value;
-                constexpr float c = (float)cos32(k1), sn = (float)sin32(k1);
-                const float2 sr = vadd(re[k1], re[32 - k1]), si = vadd(im[k1], im[32 - k1]);
-                const float2 dr = vsub(re[k1], re[32 - k1]), di = vsub(im[k1], im[32 - k1]);
-                c0r = vadd(c0r, sr); c0i = vadd(c0i, si);
-                c31r = vfmas(di, sn, vfmas(sr, c, c31r));
-                c31i = vfmas(dr, -sn, vfmas(si, c, c31i));
-            });
-            c0r = vadd(c0r, re[16]); c0i = vadd(c0i, im[16]);
-            c31r = vsub(c31r, re[16]); c31i = vsub(c31i, im[16]);
-            // real part = first pair of a transform, imaginary part = second pair
-            float* g = ob + (int64_t)4 * ch_stride;
-            g[0 * ch_stride + lane] = c31r.x * kInvN;  g[0 * ch_stride + 32 + lane] = c0r.x * kInvN;   // pair 01
-            g[3 * ch_stride + lane] = c31i.x * kInvN;  g[3 * ch_stride + 32 + lane] = c0i.x * kInvN;   // pair 12
-            g[2 * ch_stride + lane] = c31r.y * kInvN;  g[2 * ch_stride + 32 + lane] = c0r.y * kInvN;   // pair 03
-            g[5 * ch_stride + lane] = c31i.y * kInvN;  g[5 * ch_stride + 32 + lane] = c0i.y * kInvN;   // pair 23
-        }
-#endif
-#ifndef MABL_NOGCC1
-        {
-            // one transform: position p of (zr, zi) holds the input pair (z[m = 2p], z[m = 2p + 1])
-            float2 zr[16], zi[16];
-            {
-                static_for<0, 16>([&](auto pi) {
-                    constexpr int p = decltype(pi)::value;
-                    float rr[2], ii[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int k = lane + 32 * (2 * p + e);
-                        const bool up = k > 512;
-                        const int kk = up ? 1024 - k : k;
-                        const float2 z = spec[(up ? 1 : 0) * kSpecStride + kk];   // Z = P02 + i P13 as pass 0 left it (row 1: for the mirrored bin)
-                        rr[e] = z.x; ii[e] = z.y;
-                    }
-                    zr[p] = make_float2(rr[0], rr[1]); zi[p] = make_float2(ii[0], ii[1]);
-                });
-            }
-            fft32_dit(zi, zr);                                              // position q': (A[lane][q], A[lane][q + 16]), q = brev4(q')
-            float* fr = R;                                                  // two planes of 32 x 34 floats in the exchange area
-            float* fi = R + 32 * kXStride;
-            TW_FETCH();
-            static_for<0, 16>([&](auto qi) {
-                constexpr int qp = decltype(qi)::value;
-                constexpr int q = brev4(qp);
-                // table positions brev5(q) (even) and brev5(q + 16) = brev5(q) + 1 share one float4: (cos, cos', -sin, -sin')
-                const float4 w4 = TW4(brev5(q) / 2);
-                float2 r = zr[qp], i = zi[qp];
-                if constexpr (q == 0) {                                     // W^0 = 1 for n2 = 0; n2 = 16 still needs its factor
-                    const float r1 = r.y, i1 = i.y;
-                    r.y = fmaf(i1, w4.w, r1 * w4.y);
-                    i.y = fmaf(i1, w4.y, r1 * -w4.w);
-                } else {
-                    const float2 C2 = make_float2(w4.x, w4.y), S2 = make_float2(w4.z, w4.w);
-                    const float2 t = __fmul2_rn(make_float2(-r.x, -r.y), S2);
-                    r = __ffma2_rn(i, S2, __fmul2_rn(r, C2));
-                    i = __ffma2_rn(i, C2, t);
-                }
-                fr[q * kXStride + lane] = r.x; fr[(q + 16) * kXStride + lane] = r.y;
-                fi[q * kXStride + lane] = i.x; fi[(q + 16) * kXStride + lane] = i.y;
-            });
-            __syncwarp();
-            // second stage for n1 = 0 and 31, two k1 terms per packed operation
-            float2 a0r = make_float2(0.f, 0.f), a0i = a0r, a31r = a0r, a31i = a0r;
-            static_for<0, 16>([&](auto ji) {
-                constexpr int j = decltype(ji)::value;
-                const float2 pr = *reinterpret_cast<const float2*>(fr + lane * kXStride + 2 * j);   // (A'[2j], A'[2j + 1])
-                const float2 pi = *reinterpret_cast<const float2*>(fi + lane * kXStride + 2 * j);
-                constexpr int k0 = 2 * j, k1 = 2 * j + 1;
-                constexpr float c0 = (float)(k0 <= 16 ? cos32(k0) : cos32(32 - k0)), c1 = (float)(k1 <= 16 ? cos32(k1) : cos32(32 - k1));
-                constexpr float s0 = (float)(k0 <= 16 ? sin32(k0) : -sin32(32 - k0)), s1 = (float)(k1 <= 16 ? sin32(k1) : -sin32(32 - k1));
-                a0r = __fadd2_rn(a0r, pr); a0i = __fadd2_rn(a0i, pi);
-                a31r = __ffma2_rn(pi, make_float2(s0, s1), __ffma2_rn(pr, make_float2(c0, c1), a31r));
-                a31i = __ffma2_rn(pr, make_float2(-s0, -s1), __ffma2_rn(pi, make_float2(c0, c1), a31i));
-            });
-            __syncwarp();                                                   // the next frame reuses the exchange area
-            float* g = ob + (int64_t)5 * ch_stride;                         // pairs 02 and 13: planes 5 and 8
-            g[0 * ch_stride + lane] = (a31r.x + a31r.y) * kInvN;  g[0 * ch_stride + 32 + lane] = (a0r.x + a0r.y) * kInvN;
-            g[3 * ch_stride + lane] = (a31i.x + a31i.y) * kInvN;  g[3 * ch_stride + 32 + lane] = (a0i.x + a0i.y) * kInvN;
-        }
-#endif
     }
     flush_max();
 #ifdef SELD_TMEM_TABLES
